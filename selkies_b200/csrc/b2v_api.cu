@@ -1,0 +1,585 @@
+// b2v_api.cu — the C-ABI of libb2video.so (include/b2video.h): session lifecycle, the pinned BGRA
+// ingest ring, stream/event plumbing and the output thread that fires the frame callback.
+//
+// Replaces pixelflux.ScreenCapture as the reference drives it (media_pipeline.py:275-332,
+// selkies.py:3091-3189): start_capture -> b2v_create, stop_capture -> b2v_destroy,
+// update_framerate / update_video_bitrate / request_idr_frame -> b2v_set_* / b2v_request_idr.
+//
+// Per-frame flow (three streams, events in between; nothing on the host blocks except ring back-pressure):
+//   st_copy : cudaMemcpyAsync  pinned slot -> device BGRA slot                      (a) ingest
+//   st_enc  : fused CSC(+scale) -> NV12 cur ; H.264 encode kernels -> AU in HBM      (b),(c)
+//   st_out  : cudaMemcpyAsync  AU head (size + first chunk) -> pinned output slot
+//   output thread: waits the D2H event, fetches the tail of oversized AUs, runs the callback in order.
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/b2video.h"
+#include "b2v_internal.h"
+#include "h264_encoder.h"
+
+using namespace b2v;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+#define CK(call)                                                                              \
+  do { cudaError_t e_ = (call);                                                               \
+       if (e_ != cudaSuccess) return fail(B2V_ECUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+constexpr int kMaxSlots = 16;
+constexpr int kOutHead = 64;              // bytes reserved in front of the AU in the pinned output slot
+constexpr size_t kFirstChunk = 256 << 10; // AU bytes fetched speculatively with the size word
+
+struct Job {
+  int out_idx; int in_slot; int frame_id; int is_key; int64_t capture_ns; int64_t pts; int hdr_w, hdr_h;
+  bool timing;
+};
+
+struct Session {
+  b2v_settings cfg{};
+  int device = 0, sm_count = 148;
+  int src_w = 0, src_h = 0, dst_w = 0, dst_h = 0, coded_w = 0, coded_h = 0;
+  bool encode = true, timing = false;
+  cudaStream_t st_copy = nullptr, st_enc = nullptr, st_out = nullptr;
+
+  // ingest ring
+  int n_slots = 4;
+  uint8_t* host_slot[kMaxSlots] = {};
+  uint8_t* dev_slot[kMaxSlots] = {};
+  cudaEvent_t ev_h2d[kMaxSlots] = {}, ev_csc[kMaxSlots] = {};
+  bool slot_free[kMaxSlots] = {};
+  size_t frame_bytes = 0;
+  // resident frames (bench `value` leg)
+  std::vector<uint8_t*> resident;
+  // scaling taps
+  Tap *d_tx = nullptr, *d_ty = nullptr;
+  // current-frame NV12 (coded size)
+  uint8_t* d_cur = nullptr;
+  // encoder
+  Encoder* enc = nullptr;
+  // output ring
+  uint8_t* d_au[kMaxSlots] = {};
+  uint8_t* h_out[kMaxSlots] = {};
+  cudaEvent_t ev_enc[kMaxSlots] = {}, ev_out[kMaxSlots] = {};
+  bool out_free[kMaxSlots] = {};
+  size_t au_cap = 0;
+  int out_next = 0;
+
+  // frame sequencing
+  uint32_t frame_id = 0;
+  int64_t frames_since_idr = 0;
+  bool want_idr = true;
+  double fps = 60.0;
+  int bitrate_kbps = 8000;
+  int qp_fixed = 26;
+
+  // timing events (B2V_FLAG_TIMING): 8 per output slot, read back by the output thread
+  cudaEvent_t ev_t[kMaxSlots][8] = {};
+
+  b2v_cb cb = nullptr; void* user = nullptr;
+  std::mutex mu;                 // guards everything below + sequencing state
+  std::mutex submit_mu;          // serialises submitters
+  std::condition_variable cv_slot, cv_job, cv_done;
+  std::deque<Job> jobs;
+  int64_t submitted = 0, delivered = 0;
+  bool stopping = false;
+  std::thread out_thread;
+  b2v_stats stats{};
+};
+
+int round16(int v) { return (v + 15) & ~15; }
+
+int alloc_geometry(Session* s) {
+  // (re)allocate everything that depends on the frame size
+  s->coded_w = s->encode ? round16(s->dst_w) : s->dst_w;
+  s->coded_h = s->encode ? round16(s->dst_h) : s->dst_h;
+  s->frame_bytes = (size_t)s->src_w * s->src_h * 4;
+  for (int i = 0; i < s->n_slots; i++) {
+    CK(cudaHostAlloc((void**)&s->host_slot[i], s->frame_bytes, cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&s->dev_slot[i], s->frame_bytes));
+    s->slot_free[i] = true;
+  }
+  CK(cudaMalloc((void**)&s->d_cur, (size_t)s->coded_w * s->coded_h * 3 / 2));
+  if (s->dst_w != s->src_w || s->dst_h != s->src_h) {
+    std::vector<Tap> tx(s->dst_w), ty(s->dst_h);
+    make_taps_host(tx.data(), s->dst_w, s->src_w);
+    make_taps_host(ty.data(), s->dst_h, s->src_h);
+    CK(cudaMalloc((void**)&s->d_tx, sizeof(Tap) * s->dst_w));
+    CK(cudaMalloc((void**)&s->d_ty, sizeof(Tap) * s->dst_h));
+    CK(cudaMemcpy(s->d_tx, tx.data(), sizeof(Tap) * s->dst_w, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_ty, ty.data(), sizeof(Tap) * s->dst_h, cudaMemcpyHostToDevice));
+  }
+  if (s->encode) {
+    EncoderConfig ec{};
+    ec.width = s->dst_w; ec.height = s->dst_h; ec.coded_w = s->coded_w; ec.coded_h = s->coded_h;
+    ec.slice_rows = s->cfg.slice_rows > 0 ? s->cfg.slice_rows : 1;
+    ec.sm_count = s->sm_count;
+    int rc = encoder_create(&ec, &s->enc);
+    if (rc) return fail(rc, "encoder_create failed: %s", encoder_last_error());
+    s->au_cap = encoder_au_capacity(s->enc);
+    for (int i = 0; i < s->n_slots; i++) {
+      CK(cudaMalloc((void**)&s->d_au[i], s->au_cap));
+      CK(cudaHostAlloc((void**)&s->h_out[i], s->au_cap + kOutHead, cudaHostAllocDefault));
+    }
+  }
+  for (int i = 0; i < s->n_slots; i++) s->out_free[i] = true;
+  return 0;
+}
+
+void free_geometry(Session* s) {
+  for (int i = 0; i < kMaxSlots; i++) {
+    if (s->host_slot[i]) cudaFreeHost(s->host_slot[i]);
+    if (s->dev_slot[i]) cudaFree(s->dev_slot[i]);
+    if (s->d_au[i]) cudaFree(s->d_au[i]);
+    if (s->h_out[i]) cudaFreeHost(s->h_out[i]);
+    s->host_slot[i] = s->dev_slot[i] = s->d_au[i] = s->h_out[i] = nullptr;
+  }
+  for (auto p : s->resident) if (p) cudaFree(p);
+  s->resident.clear();
+  if (s->d_cur) cudaFree(s->d_cur);
+  if (s->d_tx) cudaFree(s->d_tx);
+  if (s->d_ty) cudaFree(s->d_ty);
+  s->d_cur = nullptr; s->d_tx = nullptr; s->d_ty = nullptr;
+  if (s->enc) { encoder_destroy(s->enc); s->enc = nullptr; }
+}
+
+CscParams csc_params(Session* s, const uint8_t* d_bgra, int stride, uint8_t* d_nv12) {
+  CscParams p{};
+  p.src = d_bgra; p.src_w = s->src_w; p.src_h = s->src_h; p.src_stride = stride;
+  p.dst_w = s->dst_w; p.dst_h = s->dst_h; p.coded_w = s->coded_w; p.coded_h = s->coded_h;
+  p.out_y = d_nv12; p.out_uv = d_nv12 + (size_t)s->coded_w * s->coded_h;
+  p.tx = s->d_tx; p.ty = s->d_ty;
+  return p;
+}
+
+void output_loop(Session* s) {
+  cudaSetDevice(s->device);
+  for (;;) {
+    Job j;
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv_job.wait(lk, [&] { return s->stopping || !s->jobs.empty(); });
+      if (s->jobs.empty()) { if (s->stopping) return; continue; }
+      j = s->jobs.front(); s->jobs.pop_front();
+    }
+    int size = 0, qp = 0;
+    const uint8_t* data = nullptr;
+    if (s->encode) {
+      cudaEventSynchronize(s->ev_out[j.out_idx]);
+      uint8_t* base = s->h_out[j.out_idx];
+      const AuHeader* ah = (const AuHeader*)base;     // device wrote the AU header at the start of the buffer
+      size = ah->size; qp = ah->qp;
+      if ((size_t)size + sizeof(AuHeader) > kFirstChunk && size > 0) {   // oversized AU: fetch the tail
+        size_t have = kFirstChunk;
+        cudaMemcpyAsync(base + have, s->d_au[j.out_idx] + have, sizeof(AuHeader) + (size_t)size - have, cudaMemcpyDeviceToHost, s->st_out);
+        cudaStreamSynchronize(s->st_out);
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->stats.d2h_bytes += (int64_t)(sizeof(AuHeader) + size - have);
+      }
+      uint8_t* au = base + sizeof(AuHeader);
+      data = au;
+      if (s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
+        // 10-byte stripe header written into the slack in front of the AU (AuHeader is 64 bytes; already consumed)
+        uint8_t* h = au - 10;
+        h[0] = 0x04; h[1] = j.is_key ? 1 : 0;
+        h[2] = (uint8_t)(j.frame_id >> 8); h[3] = (uint8_t)j.frame_id;
+        h[4] = 0; h[5] = 0;
+        h[6] = (uint8_t)(j.hdr_w >> 8); h[7] = (uint8_t)j.hdr_w;
+        h[8] = (uint8_t)(j.hdr_h >> 8); h[9] = (uint8_t)j.hdr_h;
+        data = h; size += 10;
+      }
+    } else {
+      cudaEventSynchronize(s->ev_enc[j.out_idx]);
+    }
+    if (j.timing) {
+      cudaEvent_t* ev = s->ev_t[j.out_idx];
+      float ms[6] = {0, 0, 0, 0, 0, 0};
+      cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+      if (s->encode) {
+        for (int k = 1; k < 5; k++) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+        cudaEventElapsedTime(&ms[5], ev[0], ev[5]);
+      } else ms[5] = ms[0];
+      std::lock_guard<std::mutex> lk(s->mu);
+      s->stats.ms_csc += ms[0]; s->stats.n_csc++;
+      if (s->encode) {
+        if (j.is_key) { s->stats.ms_intra += ms[1]; s->stats.n_intra++; }
+        else { s->stats.ms_inter += ms[1]; s->stats.n_inter++; }
+        s->stats.ms_cavlc += ms[2]; s->stats.n_cavlc++;
+        s->stats.ms_slice += ms[3]; s->stats.n_slice++;
+        s->stats.ms_pack += ms[4]; s->stats.n_pack++;
+      }
+      s->stats.ms_total_gpu += ms[5];
+    }
+    if (s->cb && s->encode) {
+      b2v_frame f{};
+      f.data = data; f.size = size; f.frame_id = j.frame_id; f.is_key = j.is_key; f.qp = qp;
+      f.pts90k = j.pts; f.capture_ns = j.capture_ns;
+      s->cb(&f, s->user);
+    }
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      if (j.in_slot >= 0) s->slot_free[j.in_slot] = true;
+      s->out_free[j.out_idx] = true;
+      s->delivered++;
+      s->stats.frames_delivered++;
+      s->stats.bytes_out += size;
+      if (j.is_key) s->stats.key_frames++;
+    }
+    s->cv_slot.notify_all();
+    s->cv_done.notify_all();
+  }
+}
+
+// common tail of b2v_ring_submit / b2v_submit_resident: CSC + encode + D2H + job
+int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, int64_t capture_ns) {
+  int out_idx = 0;
+  Job j{};
+  EncodeFrameParams fp{};
+  {
+    std::unique_lock<std::mutex> lk(s->mu);
+    out_idx = s->out_next;
+    s->cv_slot.wait(lk, [&] { return s->out_free[out_idx] || s->stopping; });
+    if (s->stopping) return fail(B2V_ESTATE, "session is stopping");
+    s->out_free[out_idx] = false;
+    s->out_next = (s->out_next + 1) % s->n_slots;
+    bool idr = s->want_idr || (s->cfg.gop > 0 && s->frames_since_idr >= s->cfg.gop);
+    s->want_idr = false;
+    s->frames_since_idr = idr ? 1 : s->frames_since_idr + 1;
+    j.out_idx = out_idx; j.in_slot = in_slot; j.frame_id = (int)(s->frame_id & 0xffff); j.is_key = idr;
+    j.capture_ns = capture_ns;
+    int ifps = (int)s->fps; if (ifps < 1) ifps = 1;
+    j.pts = (int64_t)j.frame_id * (90000 / ifps);          // media_pipeline.py:291-292
+    j.hdr_w = s->dst_w; j.hdr_h = s->dst_h; j.timing = s->timing;
+    s->frame_id++;
+    fp.idr = idr;
+    fp.rc_mode = s->cfg.rc_mode;
+    fp.qp_fixed = s->qp_fixed;
+    // target bits per frame for the device-side rate controller
+    fp.target_bits = (int64_t)((double)s->bitrate_kbps * 1000.0 / (s->fps > 0 ? s->fps : 60.0));
+    s->submitted++;
+    s->stats.frames_submitted++;
+  }
+  CscParams cp = csc_params(s, d_bgra, stride, s->d_cur);
+  cudaEvent_t* ev = s->timing ? s->ev_t[out_idx] : nullptr;
+  if (ev) cudaEventRecord(ev[0], s->st_enc);
+  int nl = launch_csc(cp, s->sm_count, s->st_enc);
+  if (ev) cudaEventRecord(ev[1], s->st_enc);
+  if (in_slot >= 0) CK(cudaEventRecord(s->ev_csc[in_slot], s->st_enc));
+  CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
+  if (s->encode) {
+    fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = ev;
+    nl += encoder_encode(s->enc, &fp, s->st_enc);
+    CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
+    CK(cudaStreamWaitEvent(s->st_out, s->ev_enc[out_idx], 0));
+    size_t first = s->au_cap < kFirstChunk ? s->au_cap : kFirstChunk;
+    CK(cudaMemcpyAsync(s->h_out[out_idx], s->d_au[out_idx], first, cudaMemcpyDeviceToHost, s->st_out));
+    CK(cudaEventRecord(s->ev_out[out_idx], s->st_out));
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->stats.d2h_bytes += (int64_t)first;
+  }
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->stats.kernel_launches += nl;
+    s->jobs.push_back(j);
+  }
+  s->cv_job.notify_one();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2v_abi_version(void) { return B2V_ABI_VERSION; }
+const char* b2v_last_error(void) { return g_err; }
+
+int b2v_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
+  if (!cfg || !out) return fail(B2V_EINVAL, "null argument");
+  int sw = cfg->src_w, sh = cfg->src_h;
+  int dw = cfg->dst_w > 0 ? cfg->dst_w : sw, dh = cfg->dst_h > 0 ? cfg->dst_h : sh;
+  if (sw < 16 || sh < 16 || sw > 7680 || sh > 4320 || (sw & 1) || (sh & 1))
+    return fail(B2V_EINVAL, "source size %dx%d unsupported (even, 16..7680 x 16..4320)", sw, sh);
+  if (dw < 16 || dh < 16 || dw > 7680 || dh > 4320 || (dw & 1) || (dh & 1))
+    return fail(B2V_EINVAL, "encoded size %dx%d unsupported", dw, dh);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(B2V_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  Session* s = new Session();
+  s->cfg = *cfg; s->device = cfg->device;
+  s->src_w = sw; s->src_h = sh; s->dst_w = dw; s->dst_h = dh;
+  s->encode = !(cfg->flags & B2V_FLAG_NO_ENCODE);
+  s->timing = (cfg->flags & B2V_FLAG_TIMING) != 0;
+  s->n_slots = cfg->ring_slots > 0 ? cfg->ring_slots : 4;
+  if (s->n_slots < 2) s->n_slots = 2;
+  if (s->n_slots > kMaxSlots) s->n_slots = kMaxSlots;
+  s->fps = cfg->fps > 0 ? cfg->fps : 60.0;
+  s->bitrate_kbps = cfg->bitrate_kbps > 0 ? cfg->bitrate_kbps : 8000;
+  s->qp_fixed = cfg->crf > 0 ? cfg->crf : 26;
+  if (s->qp_fixed > 51) s->qp_fixed = 51;
+  s->cb = cb; s->user = user;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  s->sm_count = prop.multiProcessorCount;
+  cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&s->st_enc, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking);
+  for (int i = 0; i < kMaxSlots; i++) {
+    cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_csc[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
+  }
+  for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventCreate(&s->ev_t[i][k]);
+  int rc = alloc_geometry(s);
+  if (rc) { free_geometry(s); delete s; return rc; }
+  s->out_thread = std::thread(output_loop, s);
+  *out = s;
+  return 0;
+}
+
+void b2v_destroy(void* h) {
+  if (!h) return;
+  Session* s = (Session*)h;
+  b2v_flush(h);
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->stopping = true;
+  }
+  s->cv_job.notify_all(); s->cv_slot.notify_all();
+  if (s->out_thread.joinable()) s->out_thread.join();
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  free_geometry(s);
+  for (int i = 0; i < kMaxSlots; i++) {
+    cudaEventDestroy(s->ev_h2d[i]); cudaEventDestroy(s->ev_csc[i]);
+    cudaEventDestroy(s->ev_enc[i]); cudaEventDestroy(s->ev_out[i]);
+  }
+  for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventDestroy(s->ev_t[i][k]);
+  cudaStreamDestroy(s->st_copy); cudaStreamDestroy(s->st_enc); cudaStreamDestroy(s->st_out);
+  delete s;
+}
+
+void* b2v_ring_acquire(void* h, int32_t* slot) {
+  Session* s = (Session*)h;
+  if (!s || !slot) { fail(B2V_EINVAL, "null argument"); return nullptr; }
+  std::unique_lock<std::mutex> lk(s->mu);
+  int found = -1;
+  s->cv_slot.wait(lk, [&] {
+    if (s->stopping) return true;
+    for (int i = 0; i < s->n_slots; i++) if (s->slot_free[i]) { found = i; return true; }
+    return false;
+  });
+  if (found < 0) { fail(B2V_ESTATE, "session is stopping"); return nullptr; }
+  s->slot_free[found] = false;
+  *slot = found;
+  return s->host_slot[found];
+}
+
+int b2v_ring_submit(void* h, int32_t slot, int32_t stride, int64_t capture_ns) {
+  Session* s = (Session*)h;
+  if (!s || slot < 0 || slot >= s->n_slots) return fail(B2V_EINVAL, "bad slot");
+  if (stride <= 0) stride = s->src_w * 4;
+  if (stride < s->src_w * 4 || (size_t)stride * s->src_h > s->frame_bytes) return fail(B2V_EINVAL, "stride %d does not fit the slot", stride);
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  CK(cudaMemcpyAsync(s->dev_slot[slot], s->host_slot[slot], (size_t)stride * s->src_h, cudaMemcpyHostToDevice, s->st_copy));
+  CK(cudaEventRecord(s->ev_h2d[slot], s->st_copy));
+  CK(cudaStreamWaitEvent(s->st_enc, s->ev_h2d[slot], 0));
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->stats.h2d_bytes += (int64_t)stride * s->src_h;
+  }
+  return submit_common(s, s->dev_slot[slot], stride, slot, capture_ns);
+}
+
+int b2v_resident_upload(void* h, int32_t index, const void* bgra, int32_t stride) {
+  Session* s = (Session*)h;
+  if (!s || index < 0 || index >= 1024 || !bgra) return fail(B2V_EINVAL, "bad argument");
+  if (stride <= 0) stride = s->src_w * 4;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  if ((int)s->resident.size() <= index) s->resident.resize(index + 1, nullptr);
+  if (!s->resident[index]) CK(cudaMalloc((void**)&s->resident[index], s->frame_bytes));
+  CK(cudaMemcpy2D(s->resident[index], (size_t)s->src_w * 4, bgra, stride, (size_t)s->src_w * 4, s->src_h, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b2v_submit_resident(void* h, int32_t index, int64_t capture_ns) {
+  Session* s = (Session*)h;
+  if (!s || index < 0 || index >= (int)s->resident.size() || !s->resident[index]) return fail(B2V_EINVAL, "resident frame %d not uploaded", index);
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  return submit_common(s, s->resident[index], s->src_w * 4, -1, capture_ns);
+}
+
+int b2v_flush(void* h) {
+  Session* s = (Session*)h;
+  if (!s) return fail(B2V_EINVAL, "null handle");
+  std::unique_lock<std::mutex> lk(s->mu);
+  s->cv_done.wait(lk, [&] { return s->delivered >= s->submitted; });
+  return 0;
+}
+
+int b2v_set_framerate(void* h, double fps) {
+  Session* s = (Session*)h;
+  if (!s || !(fps > 0) || fps > 1000) return fail(B2V_EINVAL, "fps out of range");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->fps = fps;
+  return 0;
+}
+int b2v_set_bitrate_kbps(void* h, int32_t kbps) {
+  Session* s = (Session*)h;
+  if (!s || kbps <= 0) return fail(B2V_EINVAL, "bitrate out of range");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->bitrate_kbps = kbps;
+  return 0;
+}
+int b2v_set_qp(void* h, int32_t qp) {
+  Session* s = (Session*)h;
+  if (!s || qp < 0 || qp > 51) return fail(B2V_EINVAL, "qp out of range");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->qp_fixed = qp;
+  return 0;
+}
+int b2v_request_idr(void* h) {
+  Session* s = (Session*)h;
+  if (!s) return fail(B2V_EINVAL, "null handle");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->want_idr = true;
+  return 0;
+}
+
+int b2v_set_resolution(void* h, int32_t sw, int32_t sh, int32_t dw, int32_t dh) {
+  Session* s = (Session*)h;
+  if (!s) return fail(B2V_EINVAL, "null handle");
+  if (dw <= 0) dw = sw;
+  if (dh <= 0) dh = sh;
+  if (sw < 16 || sh < 16 || sw > 7680 || sh > 4320 || (sw & 1) || (sh & 1) || dw < 16 || dh < 16 || dw > 7680 || dh > 4320 || (dw & 1) || (dh & 1))
+    return fail(B2V_EINVAL, "size unsupported");
+  int rc = b2v_flush(h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  free_geometry(s);
+  s->src_w = sw; s->src_h = sh; s->dst_w = dw; s->dst_h = dh;
+  rc = alloc_geometry(s);
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->want_idr = true;            // new SPS/PPS + IDR
+  s->out_next = 0;
+  return rc;
+}
+
+int b2v_get_stats(void* h, b2v_stats* out) {
+  Session* s = (Session*)h;
+  if (!s || !out) return fail(B2V_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(s->mu);
+  *out = s->stats;
+  return 0;
+}
+int b2v_reset_stats(void* h) {
+  Session* s = (Session*)h;
+  if (!s) return fail(B2V_EINVAL, "null handle");
+  std::lock_guard<std::mutex> lk(s->mu);
+  memset(&s->stats, 0, sizeof s->stats);
+  return 0;
+}
+int b2v_coded_size(void* h, int32_t* cw, int32_t* ch) {
+  Session* s = (Session*)h;
+  if (!s) return fail(B2V_EINVAL, "null handle");
+  if (cw) *cw = s->coded_w;
+  if (ch) *ch = s->coded_h;
+  return 0;
+}
+
+int b2v_csc_nv12(void* h, const void* bgra, int32_t stride, void* nv12) {
+  Session* s = (Session*)h;
+  if (!s || !bgra || !nv12) return fail(B2V_EINVAL, "null argument");
+  if (stride <= 0) stride = s->src_w * 4;
+  int rc = b2v_flush(h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  size_t out_bytes = (size_t)s->dst_w * s->dst_h * 3 / 2;
+  CK(cudaMalloc((void**)&d_in, (size_t)s->src_w * 4 * s->src_h));
+  CK(cudaMalloc((void**)&d_out, out_bytes));
+  CK(cudaMemcpy2DAsync(d_in, (size_t)s->src_w * 4, bgra, stride, (size_t)s->src_w * 4, s->src_h, cudaMemcpyHostToDevice, s->st_enc));
+  CscParams p = csc_params(s, d_in, s->src_w * 4, d_out);
+  p.coded_w = s->dst_w; p.coded_h = s->dst_h;          // visible region only
+  p.out_uv = d_out + (size_t)s->dst_w * s->dst_h;
+  launch_csc(p, s->sm_count, s->st_enc);
+  CK(cudaMemcpyAsync(nv12, d_out, out_bytes, cudaMemcpyDeviceToHost, s->st_enc));
+  CK(cudaStreamSynchronize(s->st_enc));
+  cudaFree(d_in); cudaFree(d_out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b2v_get_recon(void* h, void* nv12) {
+  Session* s = (Session*)h;
+  if (!s || !nv12) return fail(B2V_EINVAL, "null argument");
+  if (!s->encode) return fail(B2V_ESTATE, "session was created with B2V_FLAG_NO_ENCODE");
+  int rc = b2v_flush(h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->st_enc));
+  CK(cudaMemcpy(nv12, encoder_recon(s->enc), (size_t)s->coded_w * s->coded_h * 3 / 2, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b2v_bench_csc(void* h, int32_t n_resident, int32_t iters, float* ms_per_launch) {
+  Session* s = (Session*)h;
+  if (!s || n_resident <= 0 || n_resident > (int)s->resident.size() || iters <= 0 || !ms_per_launch) return fail(B2V_EINVAL, "bad argument");
+  int rc = b2v_flush(h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  // one NV12 target per resident frame so that reads AND writes cycle through > L2 of memory
+  std::vector<uint8_t*> outs(n_resident, nullptr);
+  size_t ob = (size_t)s->coded_w * s->coded_h * 3 / 2;
+  for (auto& o : outs) CK(cudaMalloc((void**)&o, ob));
+  for (int i = 0; i < n_resident; i++) {   // warm-up: one pass over every frame
+    CscParams p = csc_params(s, s->resident[i], s->src_w * 4, outs[i]);
+    launch_csc(p, s->sm_count, s->st_enc);
+  }
+  CK(cudaStreamSynchronize(s->st_enc));
+  // each launch is bracketed by its own event pair; the sum excludes host launch gaps
+  std::vector<cudaEvent_t> e0(iters), e1(iters);
+  for (int i = 0; i < iters; i++) { cudaEventCreate(&e0[i]); cudaEventCreate(&e1[i]); }
+  for (int i = 0; i < iters; i++) {
+    int k = i % n_resident;
+    CscParams p = csc_params(s, s->resident[k], s->src_w * 4, outs[k]);
+    cudaEventRecord(e0[i], s->st_enc);
+    launch_csc(p, s->sm_count, s->st_enc);
+    cudaEventRecord(e1[i], s->st_enc);
+  }
+  CK(cudaStreamSynchronize(s->st_enc));
+  double total = 0;
+  for (int i = 0; i < iters; i++) { float ms = 0; cudaEventElapsedTime(&ms, e0[i], e1[i]); total += ms; cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]); }
+  for (auto o : outs) cudaFree(o);
+  CK(cudaGetLastError());
+  *ms_per_launch = (float)(total / iters);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// csc.cu — fused BGRA -> BT.709 limited-range NV12 colour conversion (+ bilinear scale), sm_100a.
+//
+// Replaces the colour-conversion stage of the reference's native capture module
+// (pixelflux, call site src/selkies/media_pipeline.py:299-300; legacy GStreamer
+// `videoconvert`, docs/component.md:338-344).  Integer spec: DESIGN.md §3; the CPU
+// restatement it must match bit-for-bit is oracle/csc_ref.c.
+//
+// Roofline: HBM-bound streaming kernel, 4 B/px read + 1.5 B/px written (5.5 B/px algorithmic).
+//   fast path  (1:1, width % 4 == 0): one thread = 4 px x 2 rows per unit: two 16-byte loads
+//              (ld.global.nc.L1::no_allocate.v4), two 4-byte Y stores and one 4-byte CbCr store, all
+//              warp-contiguous (512 B / 128 B / 128 B per warp instruction).  U units per thread are
+//              issued back to back so 2U 16-byte loads are in flight per thread.
+//   arithmetic: dp2a (two 16-bit coefficient x 8-bit pixel MACs per instruction); rounding
+//              constant and the +16 / +128 offsets are folded into the accumulator seed.
+//   general path (scaled or ragged widths): one thread per 2x2 output block, taps from tables.
+#include "b2v_internal.h"
+
+namespace b2v {
+
+__device__ __forceinline__ int dp2a_lo(int coef, unsigned px, int acc) {
+  int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(px), "r"(acc)); return d;
+}
+__device__ __forceinline__ int dp2a_hi(int coef, unsigned px, int acc) {
+  int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(px), "r"(acc)); return d;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(uint8_t* p, unsigned v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// pixel word: byte0 = B, byte1 = G, byte2 = R, byte3 = A (ignored: coefficient 0)
+constexpr int pack16(int lo, int hi) { return (int)(((unsigned)lo & 0xffffu) | ((unsigned)hi << 16)); }
+constexpr int CY_LO = pack16(KYB, KYG), CY_HI = pack16(KYR, 0);
+constexpr int CU_LO = pack16(KUB, KUG), CU_HI = pack16(KUR, 0);
+constexpr int CV_LO = pack16(KVB, KVG), CV_HI = pack16(KVR, 0);
+constexpr int Y_SEED = (16 << 14) + (1 << 13);
+constexpr int C_SEED = (128 << 16) + (1 << 15);
+
+__device__ __forceinline__ unsigned luma(unsigned px) {
+  return (unsigned)dp2a_hi(CY_HI, px, dp2a_lo(CY_LO, px, Y_SEED)) >> 14;
+}
+__device__ __forceinline__ int chroma_acc(int clo, int chi, unsigned px, int acc) {
+  return dp2a_hi(chi, px, dp2a_lo(clo, px, acc));
+}
+__device__ __forceinline__ unsigned pack4(unsigned a, unsigned b, unsigned c, unsigned d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// 4 px x 2 rows -> Y (two u32) + CbCr (one u32 = Cb0 Cr0 Cb1 Cr1)
+__device__ __forceinline__ void convert_quad(const uint4& a, const uint4& b, unsigned& y0, unsigned& y1, unsigned& uv) {
+  y0 = pack4(luma(a.x), luma(a.y), luma(a.z), luma(a.w));
+  y1 = pack4(luma(b.x), luma(b.y), luma(b.z), luma(b.w));
+  int u0 = chroma_acc(CU_LO, CU_HI, b.y, chroma_acc(CU_LO, CU_HI, b.x, chroma_acc(CU_LO, CU_HI, a.y, chroma_acc(CU_LO, CU_HI, a.x, C_SEED))));
+  int v0 = chroma_acc(CV_LO, CV_HI, b.y, chroma_acc(CV_LO, CV_HI, b.x, chroma_acc(CV_LO, CV_HI, a.y, chroma_acc(CV_LO, CV_HI, a.x, C_SEED))));
+  int u1 = chroma_acc(CU_LO, CU_HI, b.w, chroma_acc(CU_LO, CU_HI, b.z, chroma_acc(CU_LO, CU_HI, a.w, chroma_acc(CU_LO, CU_HI, a.z, C_SEED))));
+  int v1 = chroma_acc(CV_LO, CV_HI, b.w, chroma_acc(CV_LO, CV_HI, b.z, chroma_acc(CV_LO, CV_HI, a.w, chroma_acc(CV_LO, CV_HI, a.z, C_SEED))));
+  uv = pack4((unsigned)u0 >> 16, (unsigned)v0 >> 16, (unsigned)u1 >> 16, (unsigned)v1 >> 16);
+}
+
+// ---- fast path ---------------------------------------------------------------------------
+// grid.x covers 4-px quads of a row, grid.y strides over groups of U row pairs.
+template <int U>
+__global__ void __launch_bounds__(256) csc_bgra_nv12_fast(CscParams p, int quads, int pairs) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= quads) return;
+  const uint8_t* __restrict__ src = p.src + (size_t)q * 16;
+  for (int pr0 = blockIdx.y * U; pr0 < pairs; pr0 += gridDim.y * U) {
+    uint4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int pr = pr0 + u;
+      if (pr < pairs) {
+        int r0 = min(2 * pr, p.src_h - 1), r1 = min(2 * pr + 1, p.src_h - 1);   // bottom padding rows replicate
+        a[u] = ld_stream(src + (size_t)r0 * p.src_stride);
+        b[u] = ld_stream(src + (size_t)r1 * p.src_stride);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int pr = pr0 + u;
+      if (pr < pairs) {
+        unsigned y0, y1, uv;
+        convert_quad(a[u], b[u], y0, y1, uv);
+        st_stream(p.out_y + (size_t)(2 * pr) * p.coded_w + q * 4, y0);
+        st_stream(p.out_y + (size_t)(2 * pr + 1) * p.coded_w + q * 4, y1);
+        st_stream(p.out_uv + (size_t)pr * p.coded_w + q * 4, uv);
+      }
+    }
+  }
+}
+
+// ---- general path: bilinear scale and/or ragged width, one thread per 2x2 output block -----
+__device__ __forceinline__ void fetch_bgr(const CscParams& p, int x, int y, int& B, int& G, int& R) {
+  int x0, x1, fx, y0, y1, fy;
+  if (p.tx) { Tap t = p.tx[x]; x0 = t.i0; x1 = t.i1; fx = t.f; } else { x0 = x1 = x; fx = 0; }
+  if (p.ty) { Tap t = p.ty[y]; y0 = t.i0; y1 = t.i1; fy = t.f; } else { y0 = y1 = y; fy = 0; }
+  const uint8_t* r0 = p.src + (size_t)y0 * p.src_stride;
+  const uint8_t* r1 = p.src + (size_t)y1 * p.src_stride;
+  unsigned p00 = *(const unsigned*)(r0 + x0 * 4);
+  if (fx == 0 && fy == 0) { B = p00 & 255; G = (p00 >> 8) & 255; R = (p00 >> 16) & 255; return; }
+  unsigned p01 = *(const unsigned*)(r0 + x1 * 4), p10 = *(const unsigned*)(r1 + x0 * 4), p11 = *(const unsigned*)(r1 + x1 * 4);
+  int out[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    int s = 8 * c;
+    int top = (int)((p00 >> s) & 255) * (256 - fx) + (int)((p01 >> s) & 255) * fx;
+    int bot = (int)((p10 >> s) & 255) * (256 - fx) + (int)((p11 >> s) & 255) * fx;
+    out[c] = (top * (256 - fy) + bot * fy + (1 << 15)) >> 16;
+  }
+  B = out[0]; G = out[1]; R = out[2];
+}
+
+__global__ void __launch_bounds__(256) csc_bgra_nv12_general(CscParams p) {
+  int bx = blockIdx.x * blockDim.x + threadIdx.x;   // 2x2 block column
+  int by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (bx * 2 >= p.coded_w || by * 2 >= p.coded_h) return;
+  int sb = 0, sg = 0, sr = 0;
+  unsigned yy[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int x = min(bx * 2 + (k & 1), p.dst_w - 1), y = min(by * 2 + (k >> 1), p.dst_h - 1);
+    int B, G, R;
+    fetch_bgr(p, x, y, B, G, R);
+    yy[k] = (unsigned)(KYR * R + KYG * G + KYB * B + Y_SEED) >> 14;
+    sb += B; sg += G; sr += R;
+  }
+  unsigned cb = (unsigned)(KUR * sr + KUG * sg + KUB * sb + C_SEED) >> 16;
+  unsigned cr = (unsigned)(KVR * sr + KVG * sg + KVB * sb + C_SEED) >> 16;
+  *(uint16_t*)(p.out_y + (size_t)(by * 2) * p.coded_w + bx * 2) = (uint16_t)(yy[0] | (yy[1] << 8));
+  *(uint16_t*)(p.out_y + (size_t)(by * 2 + 1) * p.coded_w + bx * 2) = (uint16_t)(yy[2] | (yy[3] << 8));
+  *(uint16_t*)(p.out_uv + (size_t)by * p.coded_w + bx * 2) = (uint16_t)(cb | (cr << 8));
+}
+
+// host side ---------------------------------------------------------------------------------
+void make_taps_host(Tap* t, int dn, int sn) {
+  for (int d = 0; d < dn; d++) {
+    if (dn == sn) { t[d] = Tap{d, d, 0, 0}; continue; }
+    int64_t pos = (((int64_t)(2 * d + 1) * sn) << 15) / dn - (1 << 15);
+    int64_t hi = (int64_t)(sn - 1) << 16;
+    if (pos < 0) pos = 0;
+    if (pos > hi) pos = hi;
+    int i0 = (int)(pos >> 16);
+    t[d] = Tap{i0, i0 + 1 < sn ? i0 + 1 : sn - 1, (int)((pos >> 8) & 255), 0};
+  }
+}
+
+static int g_csc_u = 2, g_csc_block = 160, g_csc_rows_per_block = 0;
+extern "C" void b2v_tune_csc(int u, int block, int gy) {   // bench/tuning hook (not part of the drop-in ABI)
+  if (u > 0) g_csc_u = u;
+  if (block > 0) g_csc_block = block;
+  g_csc_rows_per_block = gy;
+}
+
+int launch_csc(const CscParams& p, int sm_count, cudaStream_t st) {
+  const bool fast = p.tx == nullptr && p.ty == nullptr && p.dst_w == p.src_w && p.dst_h == p.src_h && p.coded_w == p.dst_w &&
+                    (p.coded_w % 4) == 0 && (p.src_stride % 16) == 0 && ((uintptr_t)p.src % 16) == 0 &&
+                    ((uintptr_t)p.out_y % 4) == 0 && ((uintptr_t)p.out_uv % 4) == 0;
+  if (fast) {
+    int quads = p.coded_w / 4, pairs = p.coded_h / 2;
+    int block = g_csc_block;
+    while (block > 32 && quads % block != 0 && block > 64) block -= 32;   // prefer a divisor of the row
+    if (quads % block != 0) block = g_csc_block;
+    int gx = (quads + block - 1) / block;
+    int U = g_csc_u;
+    int groups = (pairs + U - 1) / U;
+    int gy = g_csc_rows_per_block > 0 ? g_csc_rows_per_block : groups;   // default: one U-group per block
+    if (gy > groups) gy = groups;
+    if (gy > 65535) gy = 65535;
+    dim3 grid(gx, gy);
+    switch (U) {
+      case 1: csc_bgra_nv12_fast<1><<<grid, block, 0, st>>>(p, quads, pairs); break;
+      case 2: csc_bgra_nv12_fast<2><<<grid, block, 0, st>>>(p, quads, pairs); break;
+      case 3: csc_bgra_nv12_fast<3><<<grid, block, 0, st>>>(p, quads, pairs); break;
+      default: csc_bgra_nv12_fast<4><<<grid, block, 0, st>>>(p, quads, pairs); break;
+    }
+  } else {
+    dim3 block(32, 8);
+    dim3 grid((p.coded_w / 2 + 31) / 32, (p.coded_h / 2 + 7) / 8);
+    csc_bgra_nv12_general<<<grid, block, 0, st>>>(p);
+  }
+  (void)sm_count;
+  return 1;
+}
+
+}  // namespace b2v
