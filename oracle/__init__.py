@@ -58,3 +58,58 @@ def csc_nv12(bgra: np.ndarray, dst_w: int = 0, dst_h: int = 0, coded_w: int = 0,
     if rc != 0:
         raise ValueError(f"b2v_ref_csc_nv12 rc={rc}")
     return y, uv
+
+
+class RefEncoder:
+    """ctypes wrapper of oracle/h264_ref.c (one encoder instance)."""
+
+    def __init__(self, width: int, height: int, slice_rows: int = 1):
+        L = lib()
+        L.b2v_ref_enc_create.restype = C.c_void_p
+        L.b2v_ref_enc_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.b2v_ref_enc_destroy.argtypes = [C.c_void_p]
+        L.b2v_ref_enc_coded_w.argtypes = [C.c_void_p]
+        L.b2v_ref_enc_coded_h.argtypes = [C.c_void_p]
+        L.b2v_ref_enc_recon.restype = C.POINTER(C.c_uint8)
+        L.b2v_ref_enc_recon.argtypes = [C.c_void_p]
+        L.b2v_ref_enc_last_qp.argtypes = [C.c_void_p]
+        L.b2v_ref_enc_max_au.restype = C.c_size_t
+        L.b2v_ref_enc_max_au.argtypes = [C.c_void_p]
+        L.b2v_ref_enc_encode.restype = C.c_int64
+        L.b2v_ref_enc_encode.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_uint8)]
+        self.L = L
+        self.width, self.height = width, height
+        self.h = C.c_void_p(L.b2v_ref_enc_create(width, height, slice_rows))
+        self.cw, self.ch = L.b2v_ref_enc_coded_w(self.h), L.b2v_ref_enc_coded_h(self.h)
+        self._out = np.empty(L.b2v_ref_enc_max_au(self.h), np.uint8)
+
+    def encode_nv12(self, y: np.ndarray, uv: np.ndarray, idr: bool, rc_mode: int = 1, qp: int = 26, target_bits: int = 0) -> bytes:
+        assert y.shape == (self.ch, self.cw) and uv.shape == (self.ch // 2, self.cw)
+        cur = np.concatenate([y.reshape(-1), uv.reshape(-1)])
+        n = self.L.b2v_ref_enc_encode(self.h, _u8p(cur), int(idr), rc_mode, qp, target_bits, _u8p(self._out))
+        return self._out[:n].tobytes()
+
+    def encode_bgra(self, bgra: np.ndarray, idr: bool, **kw) -> bytes:
+        """oracle CSC (with padding to the coded size) + oracle encode."""
+        y, uv = csc_nv12(bgra, dst_w=self.width, dst_h=self.height, coded_w=self.cw, coded_h=self.ch)
+        return self.encode_nv12(y, uv, idr, **kw)
+
+    def recon(self):
+        p = self.L.b2v_ref_enc_recon(self.h)
+        a = np.ctypeslib.as_array(p, shape=(self.cw * self.ch * 3 // 2,)).copy()
+        return a[: self.cw * self.ch].reshape(self.ch, self.cw), a[self.cw * self.ch:].reshape(self.ch // 2, self.cw)
+
+    @property
+    def last_qp(self):
+        return self.L.b2v_ref_enc_last_qp(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.b2v_ref_enc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

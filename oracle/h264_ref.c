@@ -1,0 +1,725 @@
+/*
+ * oracle/h264_ref.c — CPU restatement of the H.264 Constrained-Baseline encoder stage.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under selkies_b200/ may link, import or execute this file;
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+ *
+ * PARITY UNPINNED: the reference (selkies @1a9cd02b) contains no encoder.  Encoding happens in the
+ * out-of-tree `pixelflux` wheel (pyproject.toml:37; media_pipeline.py:299-300) via libx264, or in
+ * GStreamer x264enc in the legacy design (docs/component.md:322).  Neither is under /root/reference,
+ * libx264 is not in this image, and the reference has no tests or golden bitstreams.  What the
+ * reference does pin is the output FORMAT, and this file follows it:
+ *   - Baseline/Constrained-Baseline, CAVLC, no B-frames, yuv420p, Annex-B, SPS/PPS in every IDR
+ *     (src/selkies/webrtc/codecs/h264.py:281-321; rtc.py:394-401 sps-pps-idr-in-keyframe=1;
+ *      webrtc/codecs/__init__.py:132-140 profile-level-id 42001f/42e01f)
+ *   - splits cleanly on 00 00 01 (h264.py:238-263) => emulation prevention is mandatory
+ * The algorithm restated is ITU-T H.264 (clauses cited inline) with this repo's own, documented
+ * encoder decisions.  Independent pin: every stream this file produces is decoded by
+ * libavcodec's h264 decoder (oracle/avdec.py) and must reproduce this encoder's reconstruction
+ * bit-for-bit (tests/test_h264_oracle.py).
+ *
+ * Encoder decisions (the "spec" the CUDA path must match bit-for-bit):
+ *   - one slice per `slice_rows` macroblock rows; deblocking disabled (disable_deblocking_filter_idc=1)
+ *   - IDR pictures: Intra16x16 only; luma mode = argmin(SAD*4 + mode) over available modes
+ *     {0 V, 1 H, 2 DC, 3 Plane}; chroma mode = argmin(SAD(Cb)+SAD(Cr))*4 + mode over {0 DC,1 H,2 V,3 Plane}
+ *   - P pictures: every macroblock P_L0_16x16 (coded as P_Skip when mv == skip predictor and cbp == 0);
+ *     full-pel exhaustive search dx in [-16,15], dy in [-16,16] against the previous reconstruction
+ *     (coordinates clamped to the coded picture), cost = SAD + lambda(qp)*(bits_se(4dx)+bits_se(4dy)),
+ *     argmin of (cost << 11 | (dy+16)*32 + (dx+16))
+ *   - quantisation: |l| = (|w|*MF + f) >> (15+qp/6), f = 2^(15+qp/6)/3 intra, /6 inter, |l| clamped to 2047
+ *   - constant QP inside a picture; picture QP from the frame-level rate controller below
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "h264_tables_ref.h"
+
+/* ------------------------------------------------------------------ bit writer (7.2, 9.1) */
+typedef struct { uint8_t* buf; size_t cap, pos; uint64_t acc; int nacc; } bitw_t;
+
+static void bw_init(bitw_t* b) { b->cap = 1 << 16; b->buf = (uint8_t*)malloc(b->cap); b->pos = 0; b->acc = 0; b->nacc = 0; }
+static void bw_free(bitw_t* b) { free(b->buf); b->buf = NULL; }
+static void bw_byte(bitw_t* b, uint8_t v) {
+  if (b->pos == b->cap) { b->cap *= 2; b->buf = (uint8_t*)realloc(b->buf, b->cap); }
+  b->buf[b->pos++] = v;
+}
+static void bw_put(bitw_t* b, int n, uint32_t v) {   /* n <= 32, MSB first */
+  if (n == 0) return;
+  if (n < 32) v &= (1u << n) - 1;
+  b->acc = (b->acc << n) | v;
+  b->nacc += n;
+  while (b->nacc >= 8) { bw_byte(b, (uint8_t)(b->acc >> (b->nacc - 8))); b->nacc -= 8; }
+}
+static void bw_ue(bitw_t* b, uint32_t v) {           /* 9.1 Exp-Golomb */
+  uint32_t x = v + 1; int len = 0;
+  while ((x >> len) > 1) len++;
+  bw_put(b, len, 0);
+  bw_put(b, len + 1, x);
+}
+static void bw_se(bitw_t* b, int v) { bw_ue(b, v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
+static size_t bw_bits(const bitw_t* b) { return b->pos * 8 + b->nacc; }
+static void bw_trailing(bitw_t* b) {                  /* 7.3.2.11 rbsp_trailing_bits */
+  bw_put(b, 1, 1);
+  if (b->nacc) bw_put(b, 8 - b->nacc, 0);
+}
+
+/* Annex B byte stream NAL unit with emulation prevention (7.4.1, B.1) */
+static size_t nal_write(uint8_t* out, int long_start, int ref_idc, int type, const uint8_t* rbsp, size_t n) {
+  size_t o = 0; int zeros = 0;
+  if (long_start) out[o++] = 0;
+  out[o++] = 0; out[o++] = 0; out[o++] = 1;
+  out[o++] = (uint8_t)((ref_idc << 5) | type);
+  for (size_t i = 0; i < n; i++) {
+    if (zeros == 2 && rbsp[i] <= 3) { out[o++] = 3; zeros = 0; }
+    out[o++] = rbsp[i];
+    zeros = rbsp[i] == 0 ? zeros + 1 : 0;
+  }
+  return o;
+}
+
+/* ------------------------------------------------------------------ encoder state */
+typedef struct {
+  int16_t coef[27][16];   /* scan-order levels: 0 luma DC (I16x16), 1..16 luma blkIdx 0..15, 17/18 chroma DC Cb/Cr, 19..22 Cb AC, 23..26 Cr AC */
+  uint8_t nnz_l[16];      /* TotalCoeff per luma 4x4 block, raster y*4+x */
+  uint8_t nnz_c[2][4];    /* per chroma 4x4 block (AC), raster y*2+x */
+  int8_t  type;           /* 0 I16x16, 1 P_L0_16x16, 2 I_PCM */
+  int8_t  i16_mode, chroma_mode;
+  uint8_t cbp;            /* luma bits 0..3, chroma << 4 */
+  int16_t mv[2];          /* quarter-sample units */
+} mb_t;
+
+typedef struct {
+  int width, height, cw, ch, mbw, mbh, slice_rows, n_slices;
+  uint8_t* recon[2];      /* NV12, coded size; recon[cur] is being written, recon[cur^1] is the reference */
+  int cur;
+  mb_t* mbs;
+  int frame_num, idr_count;
+  /* rate controller */
+  int rc_qp; int64_t rc_fullness;
+  int last_qp; int64_t last_bits;
+  uint8_t sps[64], pps[32]; int sps_len, pps_len;
+} enc_t;
+
+static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static int clip1(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+static int iabs(int v) { return v < 0 ? -v : v; }
+static int asr(int v, int s) { return v >= 0 ? (v >> s) : -((-v + (1 << s) - 1) >> s); }
+
+static int level_idc_for(int mbs) { return mbs <= 3600 ? 31 : mbs <= 8704 ? 42 : mbs <= 22080 ? 51 : mbs <= 36864 ? 52 : 62; }
+
+/* 7.3.2.1 SPS, 7.3.2.2 PPS */
+static void write_param_sets(enc_t* e) {
+  bitw_t b; bw_init(&b);
+  bw_put(&b, 8, 66);            /* profile_idc Baseline */
+  bw_put(&b, 8, 0xC0);          /* constraint_set0_flag, constraint_set1_flag => Constrained Baseline */
+  bw_put(&b, 8, level_idc_for(e->mbw * e->mbh));
+  bw_ue(&b, 0);                 /* seq_parameter_set_id */
+  bw_ue(&b, 4);                 /* log2_max_frame_num_minus4 => frame_num is 8 bits */
+  bw_ue(&b, 2);                 /* pic_order_cnt_type 2: output order == decoding order */
+  bw_ue(&b, 1);                 /* max_num_ref_frames */
+  bw_put(&b, 1, 0);             /* gaps_in_frame_num_value_allowed_flag */
+  bw_ue(&b, e->mbw - 1);
+  bw_ue(&b, e->mbh - 1);
+  bw_put(&b, 1, 1);             /* frame_mbs_only_flag */
+  bw_put(&b, 1, 1);             /* direct_8x8_inference_flag */
+  int crop_r = (e->cw - e->width) / 2, crop_b = (e->ch - e->height) / 2;
+  if (crop_r || crop_b) { bw_put(&b, 1, 1); bw_ue(&b, 0); bw_ue(&b, crop_r); bw_ue(&b, 0); bw_ue(&b, crop_b); }
+  else bw_put(&b, 1, 0);
+  bw_put(&b, 1, 0);             /* vui_parameters_present_flag */
+  bw_trailing(&b);
+  e->sps_len = (int)nal_write(e->sps, 1, 3, 7, b.buf, b.pos);
+  bw_free(&b);
+  bw_init(&b);
+  bw_ue(&b, 0); bw_ue(&b, 0);   /* pps id, sps id */
+  bw_put(&b, 1, 0);             /* entropy_coding_mode_flag: CAVLC */
+  bw_put(&b, 1, 0);             /* bottom_field_pic_order_in_frame_present_flag */
+  bw_ue(&b, 0);                 /* num_slice_groups_minus1 */
+  bw_ue(&b, 0); bw_ue(&b, 0);   /* num_ref_idx_l0/l1_default_active_minus1 */
+  bw_put(&b, 1, 0);             /* weighted_pred_flag */
+  bw_put(&b, 2, 0);             /* weighted_bipred_idc */
+  bw_se(&b, 0); bw_se(&b, 0);   /* pic_init_qp_minus26, pic_init_qs_minus26 */
+  bw_se(&b, 0);                 /* chroma_qp_index_offset */
+  bw_put(&b, 1, 1);             /* deblocking_filter_control_present_flag */
+  bw_put(&b, 1, 0);             /* constrained_intra_pred_flag */
+  bw_put(&b, 1, 0);             /* redundant_pic_cnt_present_flag */
+  bw_trailing(&b);
+  e->pps_len = (int)nal_write(e->pps, 1, 3, 8, b.buf, b.pos);
+  bw_free(&b);
+}
+
+/* ------------------------------------------------------------------ transforms (8.5) */
+static int pos_class(int raster) { int x = raster & 3, y = raster >> 2; return ((x | y) & 1) == 0 ? 0 : ((x & y) & 1) ? 1 : 2; }
+
+static void fwd4x4(const int in[16], int out[16]) {      /* W = Cf X Cf^T, rows then columns */
+  int t[16];
+  for (int i = 0; i < 4; i++) {
+    const int* r = in + 4 * i;
+    int s03 = r[0] + r[3], d03 = r[0] - r[3], s12 = r[1] + r[2], d12 = r[1] - r[2];
+    t[4 * i + 0] = s03 + s12; t[4 * i + 1] = 2 * d03 + d12; t[4 * i + 2] = s03 - s12; t[4 * i + 3] = d03 - 2 * d12;
+  }
+  for (int j = 0; j < 4; j++) {
+    int s03 = t[j] + t[12 + j], d03 = t[j] - t[12 + j], s12 = t[4 + j] + t[8 + j], d12 = t[4 + j] - t[8 + j];
+    out[j] = s03 + s12; out[4 + j] = 2 * d03 + d12; out[8 + j] = s03 - s12; out[12 + j] = d03 - 2 * d12;
+  }
+}
+static void inv4x4(const int d[16], int r[16]) {         /* 8.5.12.2: rows, then columns, (x+32)>>6 */
+  int t[16];
+  for (int i = 0; i < 4; i++) {
+    const int* p = d + 4 * i;
+    int e0 = p[0] + p[2], e1 = p[0] - p[2], e2 = (p[1] >> 1) - p[3], e3 = p[1] + (p[3] >> 1);
+    t[4 * i + 0] = e0 + e3; t[4 * i + 1] = e1 + e2; t[4 * i + 2] = e1 - e2; t[4 * i + 3] = e0 - e3;
+  }
+  for (int j = 0; j < 4; j++) {
+    int e0 = t[j] + t[8 + j], e1 = t[j] - t[8 + j], e2 = (t[4 + j] >> 1) - t[12 + j], e3 = t[4 + j] + (t[12 + j] >> 1);
+    r[j] = (e0 + e3 + 32) >> 6; r[4 + j] = (e1 + e2 + 32) >> 6; r[8 + j] = (e1 - e2 + 32) >> 6; r[12 + j] = (e0 - e3 + 32) >> 6;
+  }
+}
+static void hadamard4x4(const int in[16], int out[16]) { /* H X H, H symmetric */
+  int t[16];
+  for (int i = 0; i < 4; i++) {
+    const int* r = in + 4 * i;
+    int s01 = r[0] + r[1], d01 = r[0] - r[1], s23 = r[2] + r[3], d23 = r[2] - r[3];
+    t[4 * i + 0] = s01 + s23; t[4 * i + 1] = s01 - s23; t[4 * i + 2] = d01 - d23; t[4 * i + 3] = d01 + d23;
+  }
+  for (int j = 0; j < 4; j++) {
+    int s01 = t[j] + t[4 + j], d01 = t[j] - t[4 + j], s23 = t[8 + j] + t[12 + j], d23 = t[8 + j] - t[12 + j];
+    out[j] = s01 + s23; out[4 + j] = s01 - s23; out[8 + j] = d01 - d23; out[12 + j] = d01 + d23;
+  }
+}
+static int quant1(int w, int mf, int f, int qbits) {
+  int a = (iabs(w) * mf + f) >> qbits;
+  if (a > 2047) a = 2047;
+  return w < 0 ? -a : a;
+}
+
+/* Transform + quantise + reconstruct one 4x4 block of residual `res` (raster).
+ * levels_scan: 16 scan-order levels out (position 0 left 0 when dc_separate).
+ * dc_separate: the DC coefficient is handled by the caller (Intra16x16 / chroma): w_dc receives the
+ * forward DC; the block is reconstructed later by recon4x4() once the dequantised DC is known. */
+static void tq4x4(const int res[16], int qp, int intra, int dc_separate, int16_t levels_scan[16], int* w_dc) {
+  int w[16];
+  fwd4x4(res, w);
+  int qbits = 15 + qp / 6, f = (1 << qbits) / (intra ? 3 : 6);
+  for (int k = 0; k < 16; k++) {
+    int r = zigzag4x4[k];
+    if (k == 0 && dc_separate) { *w_dc = w[0]; levels_scan[0] = 0; continue; }
+    levels_scan[k] = (int16_t)quant1(w[r], quant_mf[qp % 6][pos_class(r)], f, qbits);
+  }
+}
+/* dequantise (8.5.12.1) + inverse transform; dc_value (already dequantised) replaces d[0] when use_dc */
+static void recon4x4(const int16_t levels_scan[16], int qp, int use_dc, int dc_value, int resid[16]) {
+  int d[16];
+  for (int k = 0; k < 16; k++) {
+    int r = zigzag4x4[k];
+    d[r] = (levels_scan[k] * dequant_v[qp % 6][pos_class(r)]) << (qp / 6);
+  }
+  if (use_dc) d[0] = dc_value;
+  inv4x4(d, resid);
+}
+static int count_nz(const int16_t* l, int from, int to) { int n = 0; for (int k = from; k < to; k++) n += l[k] != 0; return n; }
+
+/* ------------------------------------------------------------------ frame access helpers */
+static uint8_t* plane_y(enc_t* e, int idx) { return e->recon[idx]; }
+static uint8_t* plane_uv(enc_t* e, int idx) { return e->recon[idx] + (size_t)e->cw * e->ch; }
+
+static int slice_first_row(const enc_t* e, int mby) { return (mby / e->slice_rows) * e->slice_rows; }
+static int avail_top(const enc_t* e, int mby) { return mby > slice_first_row(e, mby); }
+
+/* ------------------------------------------------------------------ chroma: shared by I and P macroblocks */
+/* cur/pred: [2][64] raster 8x8 per component.  Writes levels, nnz_c, chroma cbp; reconstructs into the frame. */
+static int code_chroma(enc_t* e, mb_t* m, int mbx, int mby, int qp, int intra, const uint8_t cur[2][64], const uint8_t pred[2][64]) {
+  int qpc = chroma_qp_tab[clip3(0, 51, qp)];
+  int any_dc = 0, any_ac = 0;
+  uint8_t* uv = plane_uv(e, e->cur);
+  for (int c = 0; c < 2; c++) {
+    int dcs[4];
+    for (int b = 0; b < 4; b++) {
+      int bx = (b & 1) * 4, by = (b >> 1) * 4, res[16];
+      for (int i = 0; i < 16; i++) { int p = (by + (i >> 2)) * 8 + bx + (i & 3); res[i] = cur[c][p] - pred[c][p]; }
+      tq4x4(res, qpc, intra, 1, m->coef[19 + c * 4 + b], &dcs[b]);
+      m->nnz_c[c][b] = (uint8_t)count_nz(m->coef[19 + c * 4 + b], 1, 16);
+      any_ac |= m->nnz_c[c][b];
+    }
+    /* 2x2 DC: forward Hadamard, quantise with doubled dead zone and one more shift */
+    int t[4] = { dcs[0] + dcs[1] + dcs[2] + dcs[3], dcs[0] - dcs[1] + dcs[2] - dcs[3], dcs[0] + dcs[1] - dcs[2] - dcs[3], dcs[0] - dcs[1] - dcs[2] + dcs[3] };
+    int qbits = 15 + qpc / 6, f = (1 << qbits) / (intra ? 3 : 6);
+    int16_t* dl = m->coef[17 + c];
+    for (int k = 0; k < 4; k++) { dl[k] = (int16_t)quant1(t[k], quant_mf[qpc % 6][0], 2 * f, qbits + 1); any_dc |= dl[k] != 0; }
+    for (int k = 4; k < 16; k++) dl[k] = 0;
+    /* 8.5.11.1/2: inverse 2x2 + chroma DC dequant */
+    int fq[4] = { dl[0] + dl[1] + dl[2] + dl[3], dl[0] - dl[1] + dl[2] - dl[3], dl[0] + dl[1] - dl[2] - dl[3], dl[0] - dl[1] - dl[2] + dl[3] };
+    int ls = 16 * dequant_v[qpc % 6][0];
+    for (int b = 0; b < 4; b++) {
+      int dc = ((fq[b] * ls) << (qpc / 6)) >> 5;
+      int resid[16];
+      recon4x4(m->coef[19 + c * 4 + b], qpc, 1, dc, resid);
+      int bx = (b & 1) * 4, by = (b >> 1) * 4;
+      for (int i = 0; i < 16; i++) {
+        int y = by + (i >> 2), x = bx + (i & 3);
+        uv[(size_t)(mby * 8 + y) * e->cw + (mbx * 8 + x) * 2 + c] = (uint8_t)clip1(pred[c][y * 8 + x] + resid[i]);
+      }
+    }
+  }
+  return any_ac ? 2 : (any_dc ? 1 : 0);
+}
+
+static void load_cur(const uint8_t* nv12, int cw, int ch, int mbx, int mby, uint8_t y[256], uint8_t c[2][64]) {
+  for (int r = 0; r < 16; r++) memcpy(y + 16 * r, nv12 + (size_t)(mby * 16 + r) * cw + mbx * 16, 16);
+  const uint8_t* uv = nv12 + (size_t)cw * ch;
+  for (int r = 0; r < 8; r++)
+    for (int x = 0; x < 8; x++) {
+      c[0][r * 8 + x] = uv[(size_t)(mby * 8 + r) * cw + (mbx * 8 + x) * 2];
+      c[1][r * 8 + x] = uv[(size_t)(mby * 8 + r) * cw + (mbx * 8 + x) * 2 + 1];
+    }
+}
+
+/* ------------------------------------------------------------------ intra macroblock (8.3.3, 8.3.4) */
+static void pred16(int mode, const uint8_t* top, const uint8_t* left, int tl, int has_top, int has_left, uint8_t out[256]) {
+  if (mode == 0) { for (int y = 0; y < 16; y++) memcpy(out + 16 * y, top, 16); }
+  else if (mode == 1) { for (int y = 0; y < 16; y++) memset(out + 16 * y, left[y], 16); }
+  else if (mode == 2) {
+    int s = 0, dc;
+    if (has_top) for (int i = 0; i < 16; i++) s += top[i];
+    if (has_left) for (int i = 0; i < 16; i++) s += left[i];
+    dc = has_top && has_left ? (s + 16) >> 5 : (has_top || has_left) ? (s + 8) >> 4 : 128;
+    memset(out, dc, 256);
+  } else {
+    int H = 0, V = 0;
+    for (int i = 0; i < 8; i++) {
+      H += (i + 1) * (top[8 + i] - (i == 7 ? tl : top[6 - i]));
+      V += (i + 1) * (left[8 + i] - (i == 7 ? tl : left[6 - i]));
+    }
+    int a = 16 * (left[15] + top[15]), b = asr(5 * H + 32, 6), c = asr(5 * V + 32, 6);
+    for (int y = 0; y < 16; y++)
+      for (int x = 0; x < 16; x++) out[16 * y + x] = (uint8_t)clip1(asr(a + b * (x - 7) + c * (y - 7) + 16, 5));
+  }
+}
+static void pred8c(int mode, const uint8_t* top, const uint8_t* left, int tl, int has_top, int has_left, uint8_t out[64]) {
+  if (mode == 2) { for (int y = 0; y < 8; y++) memcpy(out + 8 * y, top, 8); }
+  else if (mode == 1) { for (int y = 0; y < 8; y++) memset(out + 8 * y, left[y], 8); }
+  else if (mode == 0) {
+    for (int b = 0; b < 4; b++) {
+      int bx = (b & 1) * 4, by = (b >> 1) * 4, st = 0, sl = 0, dc;
+      for (int i = 0; i < 4; i++) { if (has_top) st += top[bx + i]; if (has_left) sl += left[by + i]; }
+      if (b == 0 || b == 3) dc = has_top && has_left ? (st + sl + 4) >> 3 : has_top ? (st + 2) >> 2 : has_left ? (sl + 2) >> 2 : 128;
+      else if (b == 1) dc = has_top ? (st + 2) >> 2 : has_left ? (sl + 2) >> 2 : 128;
+      else dc = has_left ? (sl + 2) >> 2 : has_top ? (st + 2) >> 2 : 128;
+      for (int y = 0; y < 4; y++) memset(out + 8 * (by + y) + bx, dc, 4);
+    }
+  } else {
+    int H = 0, V = 0;
+    for (int i = 0; i < 4; i++) {
+      H += (i + 1) * (top[4 + i] - (i == 3 ? tl : top[2 - i]));
+      V += (i + 1) * (left[4 + i] - (i == 3 ? tl : left[2 - i]));
+    }
+    int a = 16 * (left[7] + top[7]), b = asr(34 * H + 32, 6), c = asr(34 * V + 32, 6);
+    for (int y = 0; y < 8; y++)
+      for (int x = 0; x < 8; x++) out[8 * y + x] = (uint8_t)clip1(asr(a + b * (x - 3) + c * (y - 3) + 16, 5));
+  }
+}
+static int sad_n(const uint8_t* a, const uint8_t* b, int n) { int s = 0; for (int i = 0; i < n; i++) s += iabs(a[i] - b[i]); return s; }
+
+static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
+  mb_t* m = &e->mbs[mby * e->mbw + mbx];
+  memset(m, 0, sizeof *m);
+  m->type = 0;
+  uint8_t cy[256], cc[2][64];
+  load_cur(cur_nv12, e->cw, e->ch, mbx, mby, cy, cc);
+  int has_left = mbx > 0, has_top = avail_top(e, mby);
+  uint8_t* ry = plane_y(e, e->cur); uint8_t* ruv = plane_uv(e, e->cur);
+  uint8_t top[16] = {0}, left[16] = {0}; int tl = 0;
+  uint8_t ctop[2][8] = {{0}}, cleft[2][8] = {{0}}; int ctl[2] = {0, 0};
+  if (has_top) {
+    memcpy(top, ry + (size_t)(mby * 16 - 1) * e->cw + mbx * 16, 16);
+    for (int x = 0; x < 8; x++) for (int c = 0; c < 2; c++) ctop[c][x] = ruv[(size_t)(mby * 8 - 1) * e->cw + (mbx * 8 + x) * 2 + c];
+  }
+  if (has_left) {
+    for (int y = 0; y < 16; y++) left[y] = ry[(size_t)(mby * 16 + y) * e->cw + mbx * 16 - 1];
+    for (int y = 0; y < 8; y++) for (int c = 0; c < 2; c++) cleft[c][y] = ruv[(size_t)(mby * 8 + y) * e->cw + (mbx * 8 - 1) * 2 + c];
+  }
+  if (has_top && has_left) {
+    tl = ry[(size_t)(mby * 16 - 1) * e->cw + mbx * 16 - 1];
+    for (int c = 0; c < 2; c++) ctl[c] = ruv[(size_t)(mby * 8 - 1) * e->cw + (mbx * 8 - 1) * 2 + c];
+  }
+  /* mode decisions */
+  uint8_t pred[256], best_pred[256]; int best_key = 1 << 30;
+  for (int mode = 0; mode < 4; mode++) {
+    if ((mode == 0 && !has_top) || (mode == 1 && !has_left) || (mode == 3 && !(has_top && has_left))) continue;
+    pred16(mode, top, left, tl, has_top, has_left, pred);
+    int key = sad_n(cy, pred, 256) * 4 + mode;
+    if (key < best_key) { best_key = key; m->i16_mode = (int8_t)mode; memcpy(best_pred, pred, 256); }
+  }
+  uint8_t cpred[2][64], best_cpred[2][64]; best_key = 1 << 30;
+  for (int mode = 0; mode < 4; mode++) {
+    if ((mode == 2 && !has_top) || (mode == 1 && !has_left) || (mode == 3 && !(has_top && has_left))) continue;
+    for (int c = 0; c < 2; c++) pred8c(mode, ctop[c], cleft[c], ctl[c], has_top, has_left, cpred[c]);
+    int key = (sad_n(cc[0], cpred[0], 64) + sad_n(cc[1], cpred[1], 64)) * 4 + mode;
+    if (key < best_key) { best_key = key; m->chroma_mode = (int8_t)mode; memcpy(best_cpred, cpred, 128); }
+  }
+  /* luma: 16 blocks, DC separated (8.5.2) */
+  int dcs[16], any_ac = 0;
+  for (int b = 0; b < 16; b++) {
+    int bx = blk_x[b] * 4, by = blk_y[b] * 4, res[16];
+    for (int i = 0; i < 16; i++) { int p = (by + (i >> 2)) * 16 + bx + (i & 3); res[i] = cy[p] - best_pred[p]; }
+    tq4x4(res, qp, 1, 1, m->coef[1 + b], &dcs[blk_y[b] * 4 + blk_x[b]]);
+    int n = count_nz(m->coef[1 + b], 1, 16);
+    m->nnz_l[blk_y[b] * 4 + blk_x[b]] = (uint8_t)n;
+    any_ac |= n;
+  }
+  int hd[16], qbits = 15 + qp / 6, f = (1 << qbits) / 3;
+  hadamard4x4(dcs, hd);
+  int dcl[16];
+  for (int k = 0; k < 16; k++) {
+    int r = zigzag4x4[k];
+    int v = asr(hd[r] + 1, 1);
+    m->coef[0][k] = (int16_t)quant1(v, quant_mf[qp % 6][0], 2 * f, qbits + 1);
+    dcl[r] = m->coef[0][k];
+  }
+  int fq[16], ls = 16 * dequant_v[qp % 6][0];
+  hadamard4x4(dcl, fq);
+  for (int b = 0; b < 16; b++) {
+    int r = blk_y[b] * 4 + blk_x[b];
+    int dc = qp >= 36 ? (fq[r] * ls) << (qp / 6 - 6) : asr(fq[r] * ls + (1 << (5 - qp / 6)), 6 - qp / 6);
+    int resid[16];
+    recon4x4(m->coef[1 + b], qp, 1, dc, resid);
+    int bx = blk_x[b] * 4, by = blk_y[b] * 4;
+    for (int i = 0; i < 16; i++) {
+      int y = by + (i >> 2), x = bx + (i & 3);
+      ry[(size_t)(mby * 16 + y) * e->cw + mbx * 16 + x] = (uint8_t)clip1(best_pred[y * 16 + x] + resid[i]);
+    }
+  }
+  int cbp_c = code_chroma(e, m, mbx, mby, qp, 1, cc, best_cpred);
+  m->cbp = (uint8_t)((any_ac ? 15 : 0) | (cbp_c << 4));
+}
+
+/* ------------------------------------------------------------------ inter macroblock (8.4) */
+static int se_bits(int v) { unsigned c = v > 0 ? 2u * v - 1 : (unsigned)(-2 * v); int len = 0; c += 1; while ((c >> len) > 1) len++; return 2 * len + 1; }
+
+static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
+  mb_t* m = &e->mbs[mby * e->mbw + mbx];
+  memset(m, 0, sizeof *m);
+  m->type = 1;
+  uint8_t cy[256], cc[2][64];
+  load_cur(cur_nv12, e->cw, e->ch, mbx, mby, cy, cc);
+  const uint8_t* refy = plane_y(e, e->cur ^ 1); const uint8_t* refuv = plane_uv(e, e->cur ^ 1);
+  int x0 = mbx * 16, y0 = mby * 16, lambda = me_lambda[qp];
+  uint32_t best = 0xffffffffu; int bdx = 0, bdy = 0;
+  for (int dy = -16; dy <= 16; dy++)
+    for (int dx = -16; dx <= 15; dx++) {
+      int sad = 0;
+      for (int r = 0; r < 16; r++) {
+        const uint8_t* rr = refy + (size_t)clip3(0, e->ch - 1, y0 + dy + r) * e->cw;
+        for (int c = 0; c < 16; c++) sad += iabs(cy[r * 16 + c] - rr[clip3(0, e->cw - 1, x0 + dx + c)]);
+      }
+      uint32_t cost = (uint32_t)(sad + lambda * (se_bits(4 * dx) + se_bits(4 * dy)));
+      uint32_t key = (cost << 11) | (uint32_t)((dy + 16) * 32 + (dx + 16));
+      if (key < best) { best = key; bdx = dx; bdy = dy; }
+    }
+  m->mv[0] = (int16_t)(4 * bdx); m->mv[1] = (int16_t)(4 * bdy);
+  /* prediction: luma full-sample copy (8.4.2.2.1 with zero fractions); chroma bilinear 1/8 (8.4.2.2.2) */
+  uint8_t py[256], pc[2][64];
+  for (int r = 0; r < 16; r++)
+    for (int c = 0; c < 16; c++) py[r * 16 + c] = refy[(size_t)clip3(0, e->ch - 1, y0 + bdy + r) * e->cw + clip3(0, e->cw - 1, x0 + bdx + c)];
+  int mvcx = 4 * bdx, mvcy = 4 * bdy, xi = mvcx >> 3, yi = mvcy >> 3, xf = mvcx & 7, yf = mvcy & 7;   /* >> on negatives: floor (checked in asr form below) */
+  xi = asr(mvcx, 3); yi = asr(mvcy, 3);
+  int cwc = e->cw / 2, chc = e->ch / 2;
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 8; c++) {
+      int xa = clip3(0, cwc - 1, mbx * 8 + xi + c), xb = clip3(0, cwc - 1, mbx * 8 + xi + c + 1);
+      int ya = clip3(0, chc - 1, mby * 8 + yi + r), yb = clip3(0, chc - 1, mby * 8 + yi + r + 1);
+      for (int k = 0; k < 2; k++) {
+        int A = refuv[(size_t)ya * e->cw + xa * 2 + k], B = refuv[(size_t)ya * e->cw + xb * 2 + k];
+        int C = refuv[(size_t)yb * e->cw + xa * 2 + k], D = refuv[(size_t)yb * e->cw + xb * 2 + k];
+        pc[k][r * 8 + c] = (uint8_t)(((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6);
+      }
+    }
+  uint8_t* ry = plane_y(e, e->cur);
+  int cbp = 0;
+  for (int b = 0; b < 16; b++) {
+    int bx = blk_x[b] * 4, by = blk_y[b] * 4, res[16], dummy;
+    for (int i = 0; i < 16; i++) { int p = (by + (i >> 2)) * 16 + bx + (i & 3); res[i] = cy[p] - py[p]; }
+    tq4x4(res, qp, 0, 0, m->coef[1 + b], &dummy);
+    int n = count_nz(m->coef[1 + b], 0, 16);
+    m->nnz_l[blk_y[b] * 4 + blk_x[b]] = (uint8_t)n;
+    if (n) cbp |= 1 << (b >> 2);
+    int resid[16];
+    recon4x4(m->coef[1 + b], qp, 0, 0, resid);
+    for (int i = 0; i < 16; i++) {
+      int y = by + (i >> 2), x = bx + (i & 3);
+      ry[(size_t)(y0 + y) * e->cw + x0 + x] = (uint8_t)clip1(py[y * 16 + x] + resid[i]);
+    }
+  }
+  int cbp_c = code_chroma(e, m, mbx, mby, qp, 0, cc, pc);
+  m->cbp = (uint8_t)(cbp | (cbp_c << 4));
+}
+
+/* ------------------------------------------------------------------ CAVLC (9.2) */
+static void cavlc_block(bitw_t* b, const int16_t* lv, int start, int maxc, int nC) {
+  /* lv[start .. start+maxc) in scan order */
+  int idx[16], n = 0;
+  for (int k = 0; k < maxc; k++) if (lv[start + k]) idx[n++] = k;
+  int total = n, t1 = 0;
+  for (int i = n - 1; i >= 0 && t1 < 3; i--) { if (iabs(lv[start + idx[i]]) == 1) t1++; else break; }
+  if (nC == -1) bw_put(b, chroma_dc_coeff_token_len[4 * total + t1], chroma_dc_coeff_token_bits[4 * total + t1]);
+  else {
+    int tab = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3;
+    bw_put(b, coeff_token_len[tab][4 * total + t1], coeff_token_bits[tab][4 * total + t1]);
+  }
+  if (!total) return;
+  for (int i = 0; i < t1; i++) bw_put(b, 1, lv[start + idx[n - 1 - i]] < 0);
+  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+  for (int i = t1; i < total; i++) {
+    int level = lv[start + idx[n - 1 - i]];
+    int code = level > 0 ? 2 * level - 2 : -2 * level - 1;
+    if (i == t1 && t1 < 3) code -= 2;
+    if (suffix_len == 0) {
+      if (code < 14) { bw_put(b, code, 0); bw_put(b, 1, 1); }
+      else if (code < 30) { bw_put(b, 14, 0); bw_put(b, 1, 1); bw_put(b, 4, code - 14); }
+      else { bw_put(b, 15, 0); bw_put(b, 1, 1); bw_put(b, 12, code - 30); }
+    } else {
+      if (code < (15 << suffix_len)) { bw_put(b, code >> suffix_len, 0); bw_put(b, 1, 1); bw_put(b, suffix_len, code & ((1 << suffix_len) - 1)); }
+      else { bw_put(b, 15, 0); bw_put(b, 1, 1); bw_put(b, 12, code - (15 << suffix_len)); }
+    }
+    if (suffix_len == 0) suffix_len = 1;
+    if (iabs(level) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+  }
+  int zeros = idx[n - 1] + 1 - total;          /* total_zeros */
+  if (total < maxc) {
+    if (nC == -1) bw_put(b, chroma_dc_total_zeros_len[total - 1][zeros], chroma_dc_total_zeros_bits[total - 1][zeros]);
+    else bw_put(b, total_zeros_len[total - 1][zeros], total_zeros_bits[total - 1][zeros]);
+  }
+  int left = zeros;
+  for (int i = n - 1; i > 0 && left > 0; i--) {
+    int run = idx[i] - idx[i - 1] - 1;
+    int t = (left > 7 ? 7 : left) - 1;
+    bw_put(b, run_len[t][run], run_bits[t][run]);
+    left -= run;
+  }
+}
+
+/* nC for luma block (bx,by in 4-sample units) / chroma block: 9.2.1 */
+static int mb_avail(const enc_t* e, int mbx, int mby, int nx, int ny) {
+  if (nx < 0 || nx >= e->mbw || ny < 0) return 0;
+  if (ny != mby && !avail_top(e, mby)) return 0;
+  (void)mbx;
+  return 1;
+}
+static int nnz_luma_at(const enc_t* e, const uint8_t* skip, int mbx, int mby, int bx, int by, int* ok) {
+  int nx = mbx, ny = mby;
+  if (bx < 0) { nx--; bx += 4; }
+  if (by < 0) { ny--; by += 4; }
+  *ok = mb_avail(e, mbx, mby, nx, ny);
+  if (!*ok) return 0;
+  const mb_t* n = &e->mbs[ny * e->mbw + nx];
+  if (skip[ny * e->mbw + nx]) return 0;
+  if (n->type == 2) return 16;
+  return n->nnz_l[by * 4 + bx];
+}
+static int nnz_chroma_at(const enc_t* e, const uint8_t* skip, int mbx, int mby, int c, int bx, int by, int* ok) {
+  int nx = mbx, ny = mby;
+  if (bx < 0) { nx--; bx += 2; }
+  if (by < 0) { ny--; by += 2; }
+  *ok = mb_avail(e, mbx, mby, nx, ny);
+  if (!*ok) return 0;
+  const mb_t* n = &e->mbs[ny * e->mbw + nx];
+  if (skip[ny * e->mbw + nx]) return 0;
+  if (n->type == 2) return 16;
+  return n->nnz_c[c][by * 2 + bx];
+}
+static int calc_nc(int na, int oka, int nb, int okb) { return oka && okb ? (na + nb + 1) >> 1 : oka ? na : okb ? nb : 0; }
+
+/* motion vector prediction for a 16x16 partition (8.4.1.3) and the P_Skip inference (8.4.1.1).
+ * Every macroblock of a P picture here is inter with refIdx 0. */
+static void mv_neighbours(const enc_t* e, int mbx, int mby, int okv[3], int mv[3][2]) {
+  int top = avail_top(e, mby);
+  int nx[3] = { mbx - 1, mbx, mbx + 1 }, ny[3] = { mby, mby - 1, mby - 1 };
+  okv[0] = mbx > 0; okv[1] = top; okv[2] = top && mbx + 1 < e->mbw;
+  if (!okv[2]) { nx[2] = mbx - 1; okv[2] = top && mbx > 0; }    /* C unavailable -> D */
+  for (int i = 0; i < 3; i++) {
+    mv[i][0] = mv[i][1] = 0;
+    if (okv[i]) { const mb_t* n = &e->mbs[ny[i] * e->mbw + nx[i]]; mv[i][0] = n->mv[0]; mv[i][1] = n->mv[1]; }
+  }
+}
+static int median3(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : (c < mn ? mn : c); }
+static void mv_pred16(const enc_t* e, int mbx, int mby, int out[2]) {
+  int ok[3], mv[3][2];
+  mv_neighbours(e, mbx, mby, ok, mv);
+  if (!ok[1] && !ok[2] && ok[0]) { out[0] = mv[0][0]; out[1] = mv[0][1]; return; }
+  int cnt = ok[0] + ok[1] + ok[2];
+  if (cnt == 1) { int i = ok[0] ? 0 : ok[1] ? 1 : 2; out[0] = mv[i][0]; out[1] = mv[i][1]; return; }
+  out[0] = median3(mv[0][0], mv[1][0], mv[2][0]);
+  out[1] = median3(mv[0][1], mv[1][1], mv[2][1]);
+}
+static void mv_pred_skip(const enc_t* e, int mbx, int mby, int out[2]) {
+  int okA = mbx > 0, okB = avail_top(e, mby);
+  out[0] = out[1] = 0;
+  if (!okA || !okB) return;
+  const mb_t* a = &e->mbs[mby * e->mbw + mbx - 1]; const mb_t* b = &e->mbs[(mby - 1) * e->mbw + mbx];
+  if ((a->mv[0] == 0 && a->mv[1] == 0) || (b->mv[0] == 0 && b->mv[1] == 0)) return;
+  mv_pred16(e, mbx, mby, out);
+}
+
+static void write_residual(const enc_t* e, bitw_t* b, const uint8_t* skip, const mb_t* m, int mbx, int mby) {
+  int oka, okb, na, nb;
+  if (m->type == 0) {   /* Intra16x16DCLevel: nC as for luma block 0 */
+    na = nnz_luma_at(e, skip, mbx, mby, -1, 0, &oka); nb = nnz_luma_at(e, skip, mbx, mby, 0, -1, &okb);
+    cavlc_block(b, m->coef[0], 0, 16, calc_nc(na, oka, nb, okb));
+  }
+  for (int blk = 0; blk < 16; blk++) {
+    if (!(m->cbp & (1 << (blk >> 2)))) continue;
+    int bx = blk_x[blk], by = blk_y[blk];
+    na = nnz_luma_at(e, skip, mbx, mby, bx - 1, by, &oka); nb = nnz_luma_at(e, skip, mbx, mby, bx, by - 1, &okb);
+    if (m->type == 0) cavlc_block(b, m->coef[1 + blk], 1, 15, calc_nc(na, oka, nb, okb));
+    else cavlc_block(b, m->coef[1 + blk], 0, 16, calc_nc(na, oka, nb, okb));
+  }
+  int cc = m->cbp >> 4;
+  if (cc) { cavlc_block(b, m->coef[17], 0, 4, -1); cavlc_block(b, m->coef[18], 0, 4, -1); }
+  if (cc & 2)
+    for (int c = 0; c < 2; c++)
+      for (int blk = 0; blk < 4; blk++) {
+        int bx = blk & 1, by = blk >> 1;
+        na = nnz_chroma_at(e, skip, mbx, mby, c, bx - 1, by, &oka); nb = nnz_chroma_at(e, skip, mbx, mby, c, bx, by - 1, &okb);
+        cavlc_block(b, m->coef[19 + c * 4 + blk], 1, 15, calc_nc(na, oka, nb, okb));
+      }
+}
+
+/* 7.3.3 slice header */
+static void write_slice_header(const enc_t* e, bitw_t* b, int first_mb, int idr, int qp) {
+  bw_ue(b, first_mb);
+  bw_ue(b, idr ? 7 : 5);                       /* slice_type: all slices of the picture I / P */
+  bw_ue(b, 0);                                 /* pic_parameter_set_id */
+  bw_put(b, 8, e->frame_num & 255);
+  if (idr) bw_ue(b, e->idr_count & 15);        /* idr_pic_id */
+  if (!idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); }   /* num_ref_idx_active_override_flag, ref_pic_list_modification_flag_l0 */
+  if (idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); }    /* no_output_of_prior_pics_flag, long_term_reference_flag */
+  else bw_put(b, 1, 0);                             /* adaptive_ref_pic_marking_mode_flag */
+  bw_se(b, qp - 26);                           /* slice_qp_delta */
+  bw_ue(b, 1);                                 /* disable_deblocking_filter_idc */
+}
+
+/* entropy-code one slice (7.3.4, 7.3.5) into a NAL appended at out; returns bytes written */
+static size_t code_slice(enc_t* e, int s, int idr, int qp, uint8_t* skip, uint8_t* out, int first_nal_of_au, int64_t* bits) {
+  bitw_t b; bw_init(&b);
+  int row0 = s * e->slice_rows, row1 = row0 + e->slice_rows; if (row1 > e->mbh) row1 = e->mbh;
+  write_slice_header(e, &b, row0 * e->mbw, idr, qp);
+  int skip_run = 0;
+  for (int mby = row0; mby < row1; mby++)
+    for (int mbx = 0; mbx < e->mbw; mbx++) {
+      const mb_t* m = &e->mbs[mby * e->mbw + mbx];
+      if (!idr) {
+        int sp[2];
+        mv_pred_skip(e, mbx, mby, sp);
+        if (m->type == 1 && m->cbp == 0 && m->mv[0] == sp[0] && m->mv[1] == sp[1]) { skip[mby * e->mbw + mbx] = 1; skip_run++; continue; }
+        bw_ue(&b, skip_run); skip_run = 0;
+      }
+      if (m->type == 0) {
+        int t = 1 + m->i16_mode + 4 * (m->cbp >> 4) + ((m->cbp & 15) ? 12 : 0);
+        bw_ue(&b, idr ? t : t + 5);
+        bw_ue(&b, m->chroma_mode);
+        bw_se(&b, 0);                          /* mb_qp_delta */
+      } else {
+        int mvp[2];
+        mv_pred16(e, mbx, mby, mvp);
+        bw_ue(&b, 0);                          /* P_L0_16x16 */
+        bw_se(&b, m->mv[0] - mvp[0]); bw_se(&b, m->mv[1] - mvp[1]);
+        bw_ue(&b, cbp_to_codenum_inter[m->cbp]);
+        if (m->cbp) bw_se(&b, 0);
+      }
+      write_residual(e, &b, skip, m, mbx, mby);
+    }
+  if (skip_run) bw_ue(&b, skip_run);
+  *bits = (int64_t)bw_bits(&b);
+  bw_trailing(&b);
+  size_t n = nal_write(out, first_nal_of_au, idr ? 3 : 2, idr ? 5 : 1, b.buf, b.pos);
+  bw_free(&b);
+  return n;
+}
+
+/* ------------------------------------------------------------------ rate control */
+static int rc_initial_qp(int64_t target_bits, int mbs) {
+  int64_t per_mb = target_bits / (mbs > 0 ? mbs : 1);
+  return per_mb >= 400 ? 22 : per_mb >= 200 ? 26 : per_mb >= 100 ? 30 : per_mb >= 50 ? 34 : per_mb >= 25 ? 38 : 42;
+}
+static void rc_update(enc_t* e, int64_t bits, int64_t target, int idr) {
+  if (target < 1) target = 1;
+  int64_t ref = idr ? 4 * target : target;
+  int64_t r = bits * 16 / ref;
+  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
+  e->rc_fullness += bits - target;
+  if (e->rc_fullness < -4 * target) e->rc_fullness = -4 * target;
+  if (e->rc_fullness > 16 * target) e->rc_fullness = 16 * target;
+  if (e->rc_fullness > 4 * target && dq < 1) dq = 1;
+  if (e->rc_fullness < -2 * target && dq > -1) dq = -1;
+  e->rc_qp = clip3(10, 48, e->rc_qp + dq);
+}
+
+/* ------------------------------------------------------------------ public API */
+void* b2v_ref_enc_create(int width, int height, int slice_rows) {
+  enc_t* e = (enc_t*)calloc(1, sizeof *e);
+  e->width = width; e->height = height;
+  e->cw = (width + 15) & ~15; e->ch = (height + 15) & ~15;
+  e->mbw = e->cw / 16; e->mbh = e->ch / 16;
+  e->slice_rows = slice_rows > 0 ? slice_rows : 1;
+  e->n_slices = (e->mbh + e->slice_rows - 1) / e->slice_rows;
+  size_t fb = (size_t)e->cw * e->ch * 3 / 2;
+  e->recon[0] = (uint8_t*)calloc(fb, 1); e->recon[1] = (uint8_t*)calloc(fb, 1);
+  e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
+  e->rc_qp = -1;
+  write_param_sets(e);
+  return e;
+}
+void b2v_ref_enc_destroy(void* h) {
+  enc_t* e = (enc_t*)h;
+  if (!e) return;
+  free(e->recon[0]); free(e->recon[1]); free(e->mbs); free(e);
+}
+int b2v_ref_enc_coded_w(void* h) { return ((enc_t*)h)->cw; }
+int b2v_ref_enc_coded_h(void* h) { return ((enc_t*)h)->ch; }
+const uint8_t* b2v_ref_enc_recon(void* h) { enc_t* e = (enc_t*)h; return e->recon[e->cur]; }
+int b2v_ref_enc_last_qp(void* h) { return ((enc_t*)h)->last_qp; }
+size_t b2v_ref_enc_max_au(void* h) { enc_t* e = (enc_t*)h; return (size_t)e->mbw * e->mbh * 1024 + 4096; }
+
+/*
+ * Encode one picture.  cur_nv12: coded_w x coded_h NV12.  rc_mode 0 = CBR (target_bits per frame,
+ * controller above), 1 = constant QP (qp_fixed).  Returns the access-unit size written to `out`.
+ */
+int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mode, int qp_fixed, int64_t target_bits, uint8_t* out) {
+  enc_t* e = (enc_t*)h;
+  int mbs = e->mbw * e->mbh;
+  if (e->rc_qp < 0) e->rc_qp = rc_initial_qp(target_bits, mbs);
+  int qp = rc_mode == 1 ? clip3(0, 51, qp_fixed) : e->rc_qp;
+  e->cur ^= 1;
+  if (idr) { e->frame_num = 0; }
+  /* phase A: analysis + reconstruction.  Intra: macroblocks of a slice are sequential (left/top
+   * dependencies), slices are independent.  Inter: every macroblock is independent. */
+  if (idr) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int s = 0; s < e->n_slices; s++) {
+      int row1 = (s + 1) * e->slice_rows; if (row1 > e->mbh) row1 = e->mbh;
+      for (int mby = s * e->slice_rows; mby < row1; mby++)
+        for (int mbx = 0; mbx < e->mbw; mbx++) encode_intra_mb(e, cur_nv12, mbx, mby, qp);
+    }
+  } else {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int mby = 0; mby < e->mbh; mby++)
+      for (int mbx = 0; mbx < e->mbw; mbx++) encode_inter_mb(e, cur_nv12, mbx, mby, qp);
+  }
+  /* phase B: entropy coding per slice, then concatenation */
+  uint8_t* skip = (uint8_t*)calloc(mbs, 1);
+  size_t per = (size_t)e->slice_rows * e->mbw * 1024 + 256;
+  uint8_t* tmp = (uint8_t*)malloc(per * e->n_slices);
+  size_t* lens = (size_t*)calloc(e->n_slices, sizeof(size_t));
+  int64_t* sbits = (int64_t*)calloc(e->n_slices, sizeof(int64_t));
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int s = 0; s < e->n_slices; s++) lens[s] = code_slice(e, s, idr, qp, skip, tmp + per * s, s == 0 && !idr, &sbits[s]);
+  size_t o = 0; int64_t bits = 0;
+  if (idr) { memcpy(out + o, e->sps, e->sps_len); o += e->sps_len; memcpy(out + o, e->pps, e->pps_len); o += e->pps_len; }
+  for (int s = 0; s < e->n_slices; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
+  free(skip); free(tmp); free(lens); free(sbits);
+  e->last_qp = qp; e->last_bits = (int64_t)o * 8;
+  if (rc_mode == 0) rc_update(e, (int64_t)o * 8, target_bits, idr);
+  if (idr) e->idr_count++;
+  e->frame_num = (e->frame_num + 1) & 255;
+  return (int64_t)o;
+}

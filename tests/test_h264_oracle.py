@@ -1,0 +1,106 @@
+"""Pins oracle/h264_ref.c against an independent decoder: every access unit decodes with libavcodec's
+h264 decoder and the decoded planes equal the encoder's own reconstruction bit-for-bit."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import avdec
+from tests import synth
+
+
+def split_nals(au: bytes):
+    """Annex-B splitter following the reference's _split_bitstream (webrtc/codecs/h264.py:238-263)."""
+    out, i = [], 0
+    while True:
+        i = au.find(b"\x00\x00\x01", i)
+        if i < 0:
+            break
+        i += 3
+        j = au.find(b"\x00\x00\x01", i)
+        if j < 0:
+            out.append(au[i:])
+            break
+        end = j - 1 if au[j - 1] == 0 else j
+        out.append(au[i:end])
+    return out
+
+
+def run(w, h, frames, qp, slice_rows=1, idr_at=(0,)):
+    enc = oracle.RefEncoder(w, h, slice_rows)
+    aus, recs = [], []
+    for i, f in enumerate(frames):
+        aus.append(enc.encode_bgra(f, i in idr_at, qp=qp))
+        recs.append(enc.recon())
+    dec = avdec.decode_stream(aus, quiet=True)
+    assert len(dec) == len(frames)
+    for (Y, U, V), (ry, ruv) in zip(dec, recs):
+        assert np.array_equal(Y, ry[:h, :w])
+        assert np.array_equal(U, ruv[: h // 2, 0:w:2])
+        assert np.array_equal(V, ruv[: h // 2, 1:w:2])
+    return aus, dec
+
+
+@pytest.mark.parametrize("qp", [0, 10, 22, 30, 40, 51])
+def test_noise_all_qps(qp):
+    run(64, 48, [synth.noise(64, 48, 1), synth.noise(64, 48, 2)], qp)
+
+
+@pytest.mark.parametrize("slice_rows", [1, 2, 3, 100])
+def test_slicing(slice_rows):
+    run(160, 96, [synth.desktop(160, 96, t) for t in range(4)], 28, slice_rows)
+    run(96, 80, [synth.bars(96, 80, t) for t in range(4)], 26, slice_rows)
+
+
+def test_cropped_sizes():
+    run(130, 70, [synth.gradient(130, 70, t) for t in range(3)], 24)     # coded 144x80, crop both ways
+    run(16, 16, [synth.noise(16, 16, 4), synth.noise(16, 16, 5)], 20)     # one macroblock
+
+
+def test_extremes_and_static():
+    w, h = 64, 64
+    black = np.zeros((h, w, 4), np.uint8)
+    white = np.full((h, w, 4), 255, np.uint8)
+    aus, _ = run(w, h, [black, black, white, white], 26)
+    assert len(aus[1]) < 200          # static frame: all skipped
+
+
+def test_idr_on_demand_and_structure():
+    frames = [synth.desktop(128, 64, t) for t in range(5)]
+    aus, _ = run(128, 64, frames, 30, idr_at=(0, 3))
+    for i, au in enumerate(aus):
+        types = [n[0] & 31 for n in split_nals(au)]
+        if i in (0, 3):
+            assert types[:2] == [7, 8] and set(types[2:]) == {5}        # SPS, PPS, IDR slices (rtc.py:394-401)
+        else:
+            assert set(types) == {1}
+        assert au[:4] == b"\x00\x00\x00\x01"
+        assert len(types) - (2 if i in (0, 3) else 0) == 4              # one slice per macroblock row
+    sps = split_nals(aus[0])[0]
+    assert sps[1] == 66 and sps[2] & 0xC0 == 0xC0                        # Constrained Baseline (h264.py:303-314)
+
+
+def test_motion_is_found():
+    """A pure translation inside the search range must cost almost nothing."""
+    base = synth.noise(256, 128, 9)
+    frames = [np.roll(base, (3 * t, 5 * t), axis=(0, 1)) for t in range(3)]
+    aus, dec = run(256, 128, frames, 28)
+    assert len(aus[1]) < len(aus[0]) // 3
+
+
+def test_psnr_reasonable():
+    f = synth.desktop(320, 192, 0)
+    aus, dec = run(320, 192, [f], 24)
+    sy, _ = oracle.csc_nv12(f)
+    assert avdec.psnr(dec[0][0], sy) > 38.0
+
+
+def test_cbr_rate_control_converges():
+    w, h, fps, kbps = 320, 192, 30, 600
+    enc = oracle.RefEncoder(w, h)
+    target = kbps * 1000 // fps
+    sizes = []
+    for t in range(40):
+        au = enc.encode_bgra(synth.desktop(w, h, t), t == 0, rc_mode=0, target_bits=target)
+        sizes.append(len(au) * 8)
+    avg = sum(sizes[10:]) / len(sizes[10:])
+    assert 0.5 * target < avg < 1.6 * target
