@@ -687,7 +687,7 @@ size_t b2v_ref_enc_max_au(void* h) { enc_t* e = (enc_t*)h; return (size_t)e->mbw
 int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mode, int qp_fixed, int64_t target_bits, uint8_t* out) {
   enc_t* e = (enc_t*)h;
   int mbs = e->mbw * e->mbh;
-  if (e->rc_qp < 0) e->rc_qp = rc_initial_qp(target_bits, mbs);
+  if (rc_mode == 0 && e->rc_qp < 0) e->rc_qp = rc_initial_qp(target_bits, mbs);
   int qp = rc_mode == 1 ? clip3(0, 51, qp_fixed) : e->rc_qp;
   e->cur ^= 1;
   if (idr) { e->frame_num = 0; }

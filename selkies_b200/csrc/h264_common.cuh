@@ -1,0 +1,307 @@
+// h264_common.cuh — device-side data layout and the per-4x4-block transform/quantise/reconstruct
+// routines shared by the intra and inter macroblock kernels.  One warp encodes one macroblock; inside
+// the warp, lane b (0..15) owns luma block blkIdx b and lanes 16..23 own the chroma blocks
+// (16..19 Cb, 20..23 Cr).  Encoder decisions follow DESIGN.md §5 (restated on the CPU by oracle/h264_ref.c).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "h264_tables.cuh"
+
+namespace b2v {
+
+constexpr int MB_I16 = 0, MB_P16 = 1, MB_PCM = 2;
+constexpr int COEF_BLOCKS = 27;            // 0 luma DC | 1..16 luma | 17,18 chroma DC | 19..26 chroma AC
+constexpr int MB_WORDS = 128;              // per-macroblock bit scratch: 128 x u32 = 4096 bits
+constexpr unsigned FULL = 0xffffffffu;
+
+struct __align__(8) MbInfo {
+  int16_t mvx, mvy;        // quarter-sample units
+  uint8_t type;            // MB_*
+  uint8_t i16_mode, chroma_mode;
+  uint8_t cbp;             // luma bits 0..3 | chroma << 4
+};
+
+struct RcState {
+  int32_t qp;              // QP for the next CBR picture (-1 = not initialised)
+  int32_t pad;
+  long long fullness;
+  int32_t last_qp;
+  int32_t frames;
+};
+
+struct FrameCtx {          // everything a kernel needs about the picture being coded
+  int cw, ch, mbw, mbh, slice_rows, n_slices;
+  int idr, rc_mode, qp_fixed;
+  long long target_bits;
+  int frame_num, idr_pic_id;
+  const uint8_t* cur;      // NV12 coded size
+  const uint8_t* ref;      // previous reconstruction (NV12)
+  uint8_t* recon;          // reconstruction being written
+  MbInfo* mbinfo;
+  int16_t* coef;           // [mbs][27][16]
+  uint8_t* nnz;            // [mbs][32]: 0..15 luma raster, 16..19 Cb, 20..23 Cr
+  uint32_t* mb_words;      // [mbs][MB_WORDS]
+  uint32_t* mb_nbits;      // [mbs]: bit count | skip flag in bit 31
+  uint32_t* slice_buf;     // [n_slices][slice_words]
+  int slice_words;
+  uint32_t* slice_size;    // [n_slices] final NAL bytes (start code + header + EP'd payload)
+  uint32_t* slice_rbsp;    // [n_slices] RBSP bytes before emulation prevention
+  long long* slice_bits;   // [n_slices]
+  int* progress;           // [mbh] intra wavefront progress counters
+  RcState* rc;
+  const uint8_t* param_sets; int param_len;   // SPS+PPS NAL bytes (IDR pictures)
+  uint8_t* au;             // AuHeader + access unit
+  int* overflow;
+};
+
+__device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(hi, max(lo, v)); }
+__device__ __forceinline__ int clip255(int v) { return min(255, max(0, v)); }
+
+__device__ __forceinline__ int rc_initial_qp(long long target_bits, int mbs) {
+  long long per_mb = target_bits / (mbs > 0 ? mbs : 1);
+  return per_mb >= 400 ? 22 : per_mb >= 200 ? 26 : per_mb >= 100 ? 30 : per_mb >= 50 ? 34 : per_mb >= 25 ? 38 : 42;
+}
+__device__ __forceinline__ int frame_qp(const FrameCtx& f) {
+  if (f.rc_mode == 1) return clip3i(0, 51, f.qp_fixed);
+  int q = f.rc->qp;
+  return q < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : q;
+}
+__device__ __forceinline__ bool top_in_slice(const FrameCtx& f, int mby) { return (mby % f.slice_rows) != 0; }
+
+__device__ __forceinline__ int pos_class(int r) { int x = r & 3, y = r >> 2; return ((x | y) & 1) == 0 ? 0 : ((x & y) & 1) ? 1 : 2; }
+
+// forward core transform, rows then columns (exact integer)
+__device__ __forceinline__ void fwd4x4(const int in[16], int out[16]) {
+  int t[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int a = in[4 * i], b = in[4 * i + 1], c = in[4 * i + 2], d = in[4 * i + 3];
+    int s03 = a + d, d03 = a - d, s12 = b + c, d12 = b - c;
+    t[4 * i] = s03 + s12; t[4 * i + 1] = 2 * d03 + d12; t[4 * i + 2] = s03 - s12; t[4 * i + 3] = d03 - 2 * d12;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int s03 = t[j] + t[12 + j], d03 = t[j] - t[12 + j], s12 = t[4 + j] + t[8 + j], d12 = t[4 + j] - t[8 + j];
+    out[j] = s03 + s12; out[4 + j] = 2 * d03 + d12; out[8 + j] = s03 - s12; out[12 + j] = d03 - 2 * d12;
+  }
+}
+// 8.5.12.2 inverse transform: rows, columns, (x + 32) >> 6
+__device__ __forceinline__ void inv4x4(const int d[16], int r[16]) {
+  int t[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int p0 = d[4 * i], p1 = d[4 * i + 1], p2 = d[4 * i + 2], p3 = d[4 * i + 3];
+    int e0 = p0 + p2, e1 = p0 - p2, e2 = (p1 >> 1) - p3, e3 = p1 + (p3 >> 1);
+    t[4 * i] = e0 + e3; t[4 * i + 1] = e1 + e2; t[4 * i + 2] = e1 - e2; t[4 * i + 3] = e0 - e3;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int e0 = t[j] + t[8 + j], e1 = t[j] - t[8 + j], e2 = (t[4 + j] >> 1) - t[12 + j], e3 = t[4 + j] + (t[12 + j] >> 1);
+    r[j] = (e0 + e3 + 32) >> 6; r[4 + j] = (e1 + e2 + 32) >> 6; r[8 + j] = (e1 - e2 + 32) >> 6; r[12 + j] = (e0 - e3 + 32) >> 6;
+  }
+}
+__device__ __forceinline__ int quant1(int w, int mf, int f, int qbits) {
+  int a = (abs(w) * mf + f) >> qbits;
+  a = min(a, 2047);
+  return w < 0 ? -a : a;
+}
+
+struct QuantParams { int mf[3]; int dq[3]; int qbits, f, qshift; };
+__device__ __forceinline__ QuantParams make_quant(int qp, bool intra) {
+  QuantParams q;
+  int m = qp % 6;
+#pragma unroll
+  for (int c = 0; c < 3; c++) { q.mf[c] = quant_mf[m][c]; q.dq[c] = dequant_v[m][c]; }
+  q.qbits = 15 + qp / 6; q.f = (1 << q.qbits) / (intra ? 3 : 6); q.qshift = qp / 6;
+  return q;
+}
+
+// scan-order position k -> raster index; evaluated at compile time inside unrolled loops
+__device__ __forceinline__ constexpr int zz(int k) {
+  return k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 4 : k == 3 ? 8 : k == 4 ? 5 : k == 5 ? 2 : k == 6 ? 3 : k == 7 ? 6 :
+         k == 8 ? 9 : k == 9 ? 12 : k == 10 ? 13 : k == 11 ? 10 : k == 12 ? 7 : k == 13 ? 11 : k == 14 ? 14 : 15;
+}
+__device__ __forceinline__ constexpr int pcls(int r) { return (((r & 3) | (r >> 2)) & 1) == 0 ? 0 : (((r & 3) & (r >> 2)) & 1) ? 1 : 2; }
+
+// Forward transform + quantise one 4x4 residual block.  lv[k]: scan-order levels.  When dc_separate the
+// DC coefficient is returned un-quantised in w_dc and lv[0] = 0.  Returns the number of non-zero levels.
+template <bool DC_SEPARATE>
+__device__ __forceinline__ int tq_block(const int res[16], const QuantParams& q, int lv[16], int& w_dc) {
+  int w[16];
+  fwd4x4(res, w);
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    if (DC_SEPARATE && k == 0) { w_dc = w[0]; lv[0] = 0; continue; }
+    lv[k] = quant1(w[zz(k)], q.mf[pcls(zz(k))], q.f, q.qbits);
+    n += lv[k] != 0;
+  }
+  return n;
+}
+// dequantise + inverse transform; when USE_DC the (already dequantised) dc replaces d[0]
+template <bool USE_DC>
+__device__ __forceinline__ void recon_block(const int lv[16], const QuantParams& q, int dc, int resid[16]) {
+  int d[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) d[zz(k)] = (lv[k] * q.dq[pcls(zz(k))]) << q.qshift;
+  if (USE_DC) d[0] = dc;
+  inv4x4(d, resid);
+}
+
+// store 16 scan-order levels as int16 (two 16-byte stores)
+__device__ __forceinline__ void store_levels(int16_t* dst, const int lv[16]) {
+  uint32_t p[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) p[i] = ((uint32_t)lv[2 * i] & 0xffffu) | ((uint32_t)lv[2 * i + 1] << 16);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  d4[0] = make_uint4(p[0], p[1], p[2], p[3]);
+  d4[1] = make_uint4(p[4], p[5], p[6], p[7]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-warp shared memory tile of one macroblock
+struct MbTile {
+  uint8_t cur_y[16][16];
+  uint8_t cur_uv[8][16];     // interleaved Cb,Cr
+  uint8_t pred_y[16][16];
+  uint8_t pred_uv[8][16];
+  uint8_t rec_y[16][16];
+  uint8_t rec_uv[8][16];
+  int dc[16];                // luma DC exchange (raster block position)
+  int dcl[16];
+};
+
+// Lanes 0..15: luma block `lane` (blkIdx), lanes 16..23: chroma.  Reads cur/pred from the tile, writes levels,
+// nnz and the reconstruction into the tile (rec_y / rec_uv), returns cbp (all lanes).
+//   INTRA16: luma DC separated + Hadamard (8.5.2 / 8.5.10), cbp luma is 0 or 15.
+template <bool INTRA16>
+__device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t* coef_mb, uint8_t* nnz_mb) {
+  const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
+  const int qpc = chroma_qp_tab[qp];
+  const QuantParams q = make_quant(is_chroma ? qpc : qp, INTRA16);
+  int lv[16], w_dc = 0, n = 0, bx = 0, by = 0, comp = 0;
+  if (is_luma) {
+    bx = blk_x[lane] * 4; by = blk_y[lane] * 4;
+    int res[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t c = *reinterpret_cast<const uint32_t*>(&t.cur_y[by + i][bx]);
+      uint32_t p = *reinterpret_cast<const uint32_t*>(&t.pred_y[by + i][bx]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) res[4 * i + j] = (int)((c >> (8 * j)) & 255) - (int)((p >> (8 * j)) & 255);
+    }
+    n = INTRA16 ? tq_block<true>(res, q, lv, w_dc) : tq_block<false>(res, q, lv, w_dc);
+  } else if (is_chroma) {
+    comp = (lane - 16) >> 2;
+    int b = (lane - 16) & 3;
+    bx = (b & 1) * 4; by = (b >> 1) * 4;
+    int res[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) res[4 * i + j] = (int)t.cur_uv[by + i][(bx + j) * 2 + comp] - (int)t.pred_uv[by + i][(bx + j) * 2 + comp];
+    n = tq_block<true>(res, q, lv, w_dc);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) lv[k] = 0;
+  }
+  // ---- DC paths -------------------------------------------------------------------------------
+  int dc_deq = 0;
+  if (INTRA16) {
+    if (is_luma) t.dc[(by >> 2) * 4 + (bx >> 2)] = w_dc;
+    __syncwarp();
+    int dl = 0;
+    if (is_luma) {   // lane r computes Hadamard output element r = (i,j): sum_ab H[i][a] d[a][b] H[b][j]
+      const int r = lane, i = r >> 2, j = r & 3;
+      int acc = 0;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          // H = [[1,1,1,1],[1,1,-1,-1],[1,-1,-1,1],[1,-1,1,-1]]
+          int ha = (i == 0) ? 1 : (i == 1) ? (a < 2 ? 1 : -1) : (i == 2) ? ((a == 0 || a == 3) ? 1 : -1) : ((a & 1) ? -1 : 1);
+          int hb = (j == 0) ? 1 : (j == 1) ? (b < 2 ? 1 : -1) : (j == 2) ? ((b == 0 || b == 3) ? 1 : -1) : ((b & 1) ? -1 : 1);
+          acc += ha * hb * t.dc[a * 4 + b];
+        }
+      int v = (acc + 1) >> 1;
+      dl = quant1(v, q.mf[0], 2 * q.f, q.qbits + 1);
+      t.dcl[r] = dl;
+    }
+    __syncwarp();
+    if (is_luma) {
+      // scan-order store of the DC levels: lane k writes level at raster zigzag4x4[k]
+      coef_mb[lane] = (int16_t)t.dcl[zigzag4x4[lane]];
+      const int r = (by >> 2) * 4 + (bx >> 2), i = r >> 2, j = r & 3;
+      int acc = 0;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          int ha = (i == 0) ? 1 : (i == 1) ? (a < 2 ? 1 : -1) : (i == 2) ? ((a == 0 || a == 3) ? 1 : -1) : ((a & 1) ? -1 : 1);
+          int hb = (j == 0) ? 1 : (j == 1) ? (b < 2 ? 1 : -1) : (j == 2) ? ((b == 0 || b == 3) ? 1 : -1) : ((b & 1) ? -1 : 1);
+          acc += ha * hb * t.dcl[a * 4 + b];
+        }
+      const int ls = 16 * q.dq[0];
+      dc_deq = qp >= 36 ? (acc * ls) << (q.qshift - 6) : (acc * ls + (1 << (5 - q.qshift))) >> (6 - q.qshift);
+    }
+  }
+  // chroma DC: 2x2 Hadamard across the 4 lanes of a component (xor-shuffles stay inside the group)
+  int cdc_level = 0;
+  {
+    int b = (lane - 16) & 3;
+    int o1 = __shfl_xor_sync(FULL, w_dc, 1), o2 = __shfl_xor_sync(FULL, w_dc, 2), o3 = __shfl_xor_sync(FULL, w_dc, 3);
+    // value of block index k seen from lane b: k = b ^ x
+    int d0, d1, d2, d3;
+    d0 = (b == 0) ? w_dc : (b == 1) ? o1 : (b == 2) ? o2 : o3;
+    d1 = (b == 1) ? w_dc : (b == 0) ? o1 : (b == 3) ? o2 : o3;
+    d2 = (b == 2) ? w_dc : (b == 3) ? o1 : (b == 0) ? o2 : o3;
+    d3 = (b == 3) ? w_dc : (b == 2) ? o1 : (b == 1) ? o2 : o3;
+    int tk = (b == 0) ? d0 + d1 + d2 + d3 : (b == 1) ? d0 - d1 + d2 - d3 : (b == 2) ? d0 + d1 - d2 - d3 : d0 - d1 - d2 + d3;
+    if (is_chroma) cdc_level = quant1(tk, q.mf[0], 2 * q.f, q.qbits + 1);
+    int l1 = __shfl_xor_sync(FULL, cdc_level, 1), l2 = __shfl_xor_sync(FULL, cdc_level, 2), l3 = __shfl_xor_sync(FULL, cdc_level, 3);
+    int c0 = (b == 0) ? cdc_level : (b == 1) ? l1 : (b == 2) ? l2 : l3;
+    int c1 = (b == 1) ? cdc_level : (b == 0) ? l1 : (b == 3) ? l2 : l3;
+    int c2 = (b == 2) ? cdc_level : (b == 3) ? l1 : (b == 0) ? l2 : l3;
+    int c3 = (b == 3) ? cdc_level : (b == 2) ? l1 : (b == 1) ? l2 : l3;
+    int fq = (b == 0) ? c0 + c1 + c2 + c3 : (b == 1) ? c0 - c1 + c2 - c3 : (b == 2) ? c0 + c1 - c2 - c3 : c0 - c1 - c2 + c3;
+    if (is_chroma) {
+      dc_deq = ((fq * (16 * q.dq[0])) << q.qshift) >> 5;
+      // chroma DC levels: coef block 17 + comp, entries 0..3 (rest zero)
+      coef_mb[(17 + comp) * 16 + b] = (int16_t)cdc_level;
+    }
+  }
+  // ---- reconstruction into the tile -------------------------------------------------------------
+  int resid[16];
+  if (is_luma) {
+    if (INTRA16) recon_block<true>(lv, q, dc_deq, resid); else recon_block<false>(lv, q, 0, resid);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t p = *reinterpret_cast<const uint32_t*>(&t.pred_y[by + i][bx]);
+      uint32_t o = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) o |= (uint32_t)clip255((int)((p >> (8 * j)) & 255) + resid[4 * i + j]) << (8 * j);
+      *reinterpret_cast<uint32_t*>(&t.rec_y[by + i][bx]) = o;
+    }
+    store_levels(coef_mb + (1 + lane) * 16, lv);
+    nnz_mb[(by >> 2) * 4 + (bx >> 2)] = (uint8_t)n;
+  } else if (is_chroma) {
+    recon_block<true>(lv, q, dc_deq, resid);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) t.rec_uv[by + i][(bx + j) * 2 + comp] = (uint8_t)clip255((int)t.pred_uv[by + i][(bx + j) * 2 + comp] + resid[4 * i + j]);
+    store_levels(coef_mb + (19 + (lane - 16)) * 16, lv);
+    nnz_mb[16 + (lane - 16)] = (uint8_t)n;
+  }
+  // ---- coded block pattern -----------------------------------------------------------------------
+  unsigned nzmask = __ballot_sync(FULL, n > 0);
+  unsigned dcmask = __ballot_sync(FULL, is_chroma && cdc_level != 0);
+  int cbp_l;
+  if (INTRA16) cbp_l = (nzmask & 0xffffu) ? 15 : 0;
+  else cbp_l = ((nzmask & 0x000fu) ? 1 : 0) | ((nzmask & 0x00f0u) ? 2 : 0) | ((nzmask & 0x0f00u) ? 4 : 0) | ((nzmask & 0xf000u) ? 8 : 0);
+  int cbp_c = (nzmask & 0xff0000u) ? 2 : (dcmask ? 1 : 0);
+  return cbp_l | (cbp_c << 4);
+}
+
+}  // namespace b2v

@@ -1,11 +1,192 @@
-// placeholder; replaced by the real encoder
+// h264_encoder.cu — host side of the H.264 Constrained-Baseline encoder: parameter sets (7.3.2.1/2),
+// HBM buffers, per-picture sequencing (frame_num, idr_pic_id, reference swap) and the kernel pipeline
+//   [k_intra_rows | k_inter_mb] -> k_cavlc_mb -> k_slice_bits -> k_pack_au
+// The output format is what the reference's consumers require: Annex-B, CAVLC,
+// no B-frames, 4:2:0, in-band SPS/PPS on every IDR (src/selkies/rtc.py:394-401,
+// src/selkies/webrtc/codecs/h264.py:281-321).
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "h264_common.cuh"
 #include "h264_encoder.h"
+#include "h264_kernels.h"
+
 namespace b2v {
-struct Encoder { int dummy; };
-int encoder_create(const EncoderConfig*, Encoder**) { return -4; }
-void encoder_destroy(Encoder*) {}
-size_t encoder_au_capacity(const Encoder*) { return 0; }
-int encoder_encode(Encoder*, const EncodeFrameParams*, cudaStream_t) { return 0; }
-const uint8_t* encoder_recon(const Encoder*) { return nullptr; }
-const char* encoder_last_error() { return "encoder not built yet"; }
+
+int launch_pack_cap(const FrameCtx& f, long long au_cap, cudaStream_t st);
+
+static thread_local char g_enc_err[256] = "";
+const char* encoder_last_error() { return g_enc_err; }
+
+struct Encoder {
+  EncoderConfig cfg{};
+  int mbw = 0, mbh = 0, n_slices = 0;
+  uint8_t* recon[2] = {nullptr, nullptr};
+  int cur = 0;
+  MbInfo* mbinfo = nullptr;
+  int16_t* coef = nullptr;
+  uint8_t* nnz = nullptr;
+  uint32_t *mb_words = nullptr, *mb_nbits = nullptr, *slice_buf = nullptr, *slice_size = nullptr, *slice_rbsp = nullptr;
+  long long* slice_bits = nullptr;
+  int slice_words = 0;
+  int* progress = nullptr;
+  int* overflow = nullptr;
+  RcState* rc = nullptr;
+  uint8_t* param_sets = nullptr; int param_len = 0;
+  size_t au_cap = 0;
+  int frame_num = 0, idr_count = 0;
+  bool have_ref = false;
+};
+
+namespace {
+
+struct HostBits {
+  std::vector<uint8_t> buf; uint64_t acc = 0; int n = 0;
+  void put(int len, uint32_t v) {
+    if (!len) return;
+    if (len < 32) v &= (1u << len) - 1;
+    acc = (acc << len) | v; n += len;
+    while (n >= 8) { buf.push_back((uint8_t)(acc >> (n - 8))); n -= 8; }
+  }
+  void ue(uint32_t v) { uint32_t x = v + 1; int len = 0; while ((x >> len) > 1) len++; put(len, 0); put(len + 1, x); }
+  void se(int v) { ue(v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
+  void trailing() { put(1, 1); if (n) put(8 - n, 0); }
+};
+
+void append_nal(std::vector<uint8_t>& out, int ref_idc, int type, const std::vector<uint8_t>& rbsp) {
+  out.insert(out.end(), {0, 0, 0, 1});
+  out.push_back((uint8_t)((ref_idc << 5) | type));
+  int zeros = 0;
+  for (uint8_t b : rbsp) {
+    if (zeros == 2 && b <= 3) { out.push_back(3); zeros = 0; }
+    out.push_back(b);
+    zeros = b == 0 ? zeros + 1 : 0;
+  }
 }
+
+int level_idc_for(int mbs) { return mbs <= 3600 ? 31 : mbs <= 8704 ? 42 : mbs <= 22080 ? 51 : mbs <= 36864 ? 52 : 62; }
+
+std::vector<uint8_t> make_param_sets(const EncoderConfig& c, int mbw, int mbh) {
+  std::vector<uint8_t> out;
+  HostBits b;
+  b.put(8, 66); b.put(8, 0xC0); b.put(8, (uint32_t)level_idc_for(mbw * mbh));
+  b.ue(0);                 // seq_parameter_set_id
+  b.ue(4);                 // log2_max_frame_num_minus4
+  b.ue(2);                 // pic_order_cnt_type
+  b.ue(1);                 // max_num_ref_frames
+  b.put(1, 0);             // gaps_in_frame_num_value_allowed_flag
+  b.ue(mbw - 1); b.ue(mbh - 1);
+  b.put(1, 1);             // frame_mbs_only_flag
+  b.put(1, 1);             // direct_8x8_inference_flag
+  const int crop_r = (c.coded_w - c.width) / 2, crop_b = (c.coded_h - c.height) / 2;
+  if (crop_r || crop_b) { b.put(1, 1); b.ue(0); b.ue(crop_r); b.ue(0); b.ue(crop_b); } else b.put(1, 0);
+  b.put(1, 0);             // vui_parameters_present_flag
+  b.trailing();
+  append_nal(out, 3, 7, b.buf);
+  HostBits p;
+  p.ue(0); p.ue(0);
+  p.put(1, 0);             // entropy_coding_mode_flag (CAVLC)
+  p.put(1, 0);             // bottom_field_pic_order_in_frame_present_flag
+  p.ue(0);                 // num_slice_groups_minus1
+  p.ue(0); p.ue(0);        // num_ref_idx_l0/l1_default_active_minus1
+  p.put(1, 0); p.put(2, 0);
+  p.se(0); p.se(0); p.se(0);
+  p.put(1, 1);             // deblocking_filter_control_present_flag
+  p.put(1, 0);             // constrained_intra_pred_flag
+  p.put(1, 0);             // redundant_pic_cnt_present_flag
+  p.trailing();
+  append_nal(out, 3, 8, p.buf);
+  return out;
+}
+
+}  // namespace
+
+#define ECK(call)                                                                                        \
+  do { cudaError_t e_ = (call);                                                                          \
+       if (e_ != cudaSuccess) { snprintf(g_enc_err, sizeof g_enc_err, "%s -> %s", #call, cudaGetErrorString(e_)); encoder_destroy(e); return -2; } \
+  } while (0)
+
+int encoder_create(const EncoderConfig* cfg, Encoder** out) {
+  if (!cfg || !out || (cfg->coded_w & 15) || (cfg->coded_h & 15) || cfg->slice_rows < 1) {
+    snprintf(g_enc_err, sizeof g_enc_err, "bad encoder config");
+    return -1;
+  }
+  Encoder* e = new Encoder();
+  e->cfg = *cfg;
+  e->mbw = cfg->coded_w / 16; e->mbh = cfg->coded_h / 16;
+  e->n_slices = (e->mbh + cfg->slice_rows - 1) / cfg->slice_rows;
+  const size_t mbs = (size_t)e->mbw * e->mbh, fb = (size_t)cfg->coded_w * cfg->coded_h * 3 / 2;
+  ECK(cudaMalloc((void**)&e->recon[0], fb));
+  ECK(cudaMalloc((void**)&e->recon[1], fb));
+  ECK(cudaMemset(e->recon[0], 0, fb));
+  ECK(cudaMemset(e->recon[1], 0, fb));
+  ECK(cudaMalloc((void**)&e->mbinfo, mbs * sizeof(MbInfo)));
+  ECK(cudaMalloc((void**)&e->coef, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
+  ECK(cudaMemset(e->coef, 0, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
+  ECK(cudaMalloc((void**)&e->nnz, mbs * 32));
+  ECK(cudaMemset(e->nnz, 0, mbs * 32));
+  ECK(cudaMalloc((void**)&e->mb_words, mbs * MB_WORDS * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->mb_nbits, mbs * sizeof(uint32_t)));
+  e->slice_words = cfg->slice_rows * e->mbw * MB_WORDS + 64;
+  ECK(cudaMalloc((void**)&e->slice_buf, (size_t)e->n_slices * e->slice_words * sizeof(uint32_t)));
+  ECK(cudaMemset(e->slice_buf, 0, (size_t)e->n_slices * e->slice_words * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->slice_size, e->n_slices * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->slice_rbsp, e->n_slices * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->slice_bits, e->n_slices * sizeof(long long)));
+  ECK(cudaMalloc((void**)&e->progress, e->mbh * sizeof(int)));
+  ECK(cudaMalloc((void**)&e->overflow, sizeof(int)));
+  ECK(cudaMemset(e->overflow, 0, sizeof(int)));
+  ECK(cudaMalloc((void**)&e->rc, sizeof(RcState)));
+  RcState rc0{}; rc0.qp = -1;
+  ECK(cudaMemcpy(e->rc, &rc0, sizeof rc0, cudaMemcpyHostToDevice));
+  std::vector<uint8_t> ps = make_param_sets(*cfg, e->mbw, e->mbh);
+  e->param_len = (int)ps.size();
+  ECK(cudaMalloc((void**)&e->param_sets, ps.size()));
+  ECK(cudaMemcpy(e->param_sets, ps.data(), ps.size(), cudaMemcpyHostToDevice));
+  e->au_cap = sizeof(AuHeader) + ps.size() + (size_t)e->n_slices * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
+  *out = e;
+  return 0;
+}
+
+void encoder_destroy(Encoder* e) {
+  if (!e) return;
+  void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo, e->coef, e->nnz, e->mb_words, e->mb_nbits, e->slice_buf, e->slice_size,
+                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete e;
+}
+
+size_t encoder_au_capacity(const Encoder* e) { return e->au_cap; }
+const uint8_t* encoder_recon(const Encoder* e) { return e->recon[e->cur]; }
+
+int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
+  const bool idr = p->idr || !e->have_ref;
+  e->cur ^= 1;
+  if (idr) e->frame_num = 0;
+  FrameCtx f{};
+  f.cw = e->cfg.coded_w; f.ch = e->cfg.coded_h; f.mbw = e->mbw; f.mbh = e->mbh;
+  f.slice_rows = e->cfg.slice_rows; f.n_slices = e->n_slices;
+  f.idr = idr; f.rc_mode = p->rc_mode; f.qp_fixed = p->qp_fixed; f.target_bits = p->target_bits;
+  f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count;
+  f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
+  f.mbinfo = e->mbinfo; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits;
+  f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
+  f.slice_bits = e->slice_bits; f.progress = e->progress; f.rc = e->rc;
+  f.param_sets = e->param_sets; f.param_len = e->param_len; f.au = p->au; f.overflow = e->overflow;
+  int n = 0;
+  n += idr ? launch_intra(f, st) : launch_inter(f, st);
+  if (p->ev) cudaEventRecord(p->ev[2], st);
+  n += launch_cavlc(f, st);
+  if (p->ev) cudaEventRecord(p->ev[3], st);
+  n += launch_slice(f, st);
+  if (p->ev) cudaEventRecord(p->ev[4], st);
+  n += launch_pack_cap(f, (long long)e->au_cap, st);
+  if (p->ev) cudaEventRecord(p->ev[5], st);
+  if (idr) e->idr_count++;
+  e->frame_num = (e->frame_num + 1) & 255;
+  e->have_ref = true;
+  return n;
+}
+
+}  // namespace b2v

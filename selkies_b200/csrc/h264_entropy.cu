@@ -1,0 +1,495 @@
+// h264_entropy.cu — CAVLC entropy coding and byte-stream assembly (ITU-T H.264 7.3.4/7.3.5, 9.2, Annex B).
+//
+// Entropy coding is serial per slice in the bitstream, but nothing a macroblock writes depends on the
+// BITS of its neighbours — only on their coefficient counts (nC) and motion vectors, which the
+// analysis kernels already left in HBM.  So it is split into three data-parallel kernels:
+//   k_cavlc_mb    one warp per macroblock, one LANE per residual block (27 blocks): each lane sizes its
+//                 block, a warp prefix-sum places it, then it writes its codes with shared-memory atomicOr;
+//                 result: a private bit string per macroblock (+ P_Skip decision, mvd from 8.4.1.3 prediction)
+//   k_slice_bits  one block per slice: block-wide scans give every macroblock its bit offset and its
+//                 mb_skip_run; macroblock bit strings are shifted into the slice RBSP; counts the
+//                 emulation-prevention bytes the slice will need
+//   k_pack_au     one block per slice: prefix over slice sizes, emulation prevention (parallel rule: a 03 is
+//                 inserted before byte i iff byte<=3 and the run of zero bytes before it is even and >=2),
+//                 start codes + NAL headers, AuHeader, and the frame-level rate-controller update.
+// CPU restatement: oracle/h264_ref.c cavlc_block(), code_slice(), nal_write(), rc_update().
+#include "h264_common.cuh"
+#include "h264_encoder.h"
+#include "h264_kernels.h"
+
+namespace b2v {
+
+// ------------------------------------------------------------------------------------------------ bit sinks
+struct CountSink {
+  int n = 0;
+  __device__ __forceinline__ void put(int len, uint32_t) { n += len; }
+};
+struct SmemSink {           // MSB-first into big-endian u32 words, concurrent writers use atomicOr
+  uint32_t* w; int pos; int cap_bits;
+  __device__ __forceinline__ void put(int len, uint32_t v) {
+    if (len == 0) return;
+    if (pos + len <= cap_bits) {
+      const int wi = pos >> 5, o = pos & 31, space = 32 - o;
+      if (len <= space) atomicOr(&w[wi], v << (space - len));
+      else { atomicOr(&w[wi], v >> (len - space)); atomicOr(&w[wi + 1], v << (32 - (len - space))); }
+    }
+    pos += len;
+  }
+};
+template <class S> __device__ __forceinline__ void put_ue(S& s, uint32_t v) { const int len = 31 - __clz(v + 1); s.put(2 * len + 1, v + 1); }
+template <class S> __device__ __forceinline__ void put_se(S& s, int v) { put_ue(s, v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
+__device__ __forceinline__ int ue_len(uint32_t v) { return 2 * (31 - __clz(v + 1)) + 1; }
+
+// ------------------------------------------------------------------------------------------------ residual block (9.2)
+template <class S>
+__device__ __forceinline__ void cavlc_block(S& s, const int16_t* lv /* scan order, already offset by start */, int maxc, int nC) {
+  uint32_t nz = 0, ones = 0;
+  for (int k = 0; k < maxc; k++) { const int v = lv[k]; nz |= (uint32_t)(v != 0) << k; ones |= (uint32_t)(v == 1 || v == -1) << k; }
+  const int total = __popc(nz);
+  int t1 = 0;
+  { uint32_t m = nz; while (m && t1 < 3) { const int top = 31 - __clz(m); if (!((ones >> top) & 1)) break; t1++; m ^= 1u << top; } }
+  if (nC < 0) s.put(chroma_dc_coeff_token_len[4 * total + t1], chroma_dc_coeff_token_bits[4 * total + t1]);
+  else { const int tab = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3; s.put(coeff_token_len[tab][4 * total + t1], coeff_token_bits[tab][4 * total + t1]); }
+  if (!total) return;
+  uint32_t m = nz;
+  for (int i = 0; i < t1; i++) { const int top = 31 - __clz(m); s.put(1, lv[top] < 0 ? 1u : 0u); m ^= 1u << top; }
+  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+  bool first = true;
+  while (m) {
+    const int top = 31 - __clz(m); m ^= 1u << top;
+    const int level = lv[top];
+    int code = level > 0 ? 2 * level - 2 : -2 * level - 1;
+    if (first && t1 < 3) code -= 2;
+    first = false;
+    if (suffix_len == 0) {
+      if (code < 14) s.put(code + 1, 1);
+      else if (code < 30) { s.put(15, 1); s.put(4, (uint32_t)(code - 14)); }
+      else { s.put(16, 1); s.put(12, (uint32_t)(code - 30)); }
+    } else {
+      if (code < (15 << suffix_len)) { s.put((code >> suffix_len) + 1, 1); s.put(suffix_len, (uint32_t)(code & ((1 << suffix_len) - 1))); }
+      else { s.put(16, 1); s.put(12, (uint32_t)(code - (15 << suffix_len))); }
+    }
+    if (suffix_len == 0) suffix_len = 1;
+    if (abs(level) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+  }
+  const int zeros = (31 - __clz(nz)) + 1 - total;
+  if (total < maxc) {
+    if (nC < 0) s.put(chroma_dc_total_zeros_len[total - 1][zeros], chroma_dc_total_zeros_bits[total - 1][zeros]);
+    else s.put(total_zeros_len[total - 1][zeros], total_zeros_bits[total - 1][zeros]);
+  }
+  int left = zeros;
+  m = nz;
+  while (left > 0 && (m & (m - 1))) {
+    const int top = 31 - __clz(m); m ^= 1u << top;
+    const int run = top - (31 - __clz(m)) - 1;
+    const int tix = min(left, 7) - 1;
+    s.put(run_len[tix][run], run_bits[tix][run]);
+    left -= run;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ mv prediction (8.4.1.3, 8.4.1.1)
+__device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+struct MvCtx { bool okA, okB, okC; int ax, ay, bx, by, cx, cy; };
+__device__ __forceinline__ MvCtx mv_ctx(const FrameCtx& f, int mbx, int mby) {
+  MvCtx m;
+  const bool top = top_in_slice(f, mby);
+  m.okA = mbx > 0; m.okB = top; m.okC = top && mbx + 1 < f.mbw;
+  int cxi = mbx + 1;
+  if (!m.okC) { cxi = mbx - 1; m.okC = top && mbx > 0; }      // C unavailable -> D
+  m.ax = m.ay = m.bx = m.by = m.cx = m.cy = 0;
+  if (m.okA) { const MbInfo a = f.mbinfo[mby * f.mbw + mbx - 1]; m.ax = a.mvx; m.ay = a.mvy; }
+  if (m.okB) { const MbInfo b = f.mbinfo[(mby - 1) * f.mbw + mbx]; m.bx = b.mvx; m.by = b.mvy; }
+  if (m.okC) { const MbInfo c = f.mbinfo[(mby - 1) * f.mbw + cxi]; m.cx = c.mvx; m.cy = c.mvy; }
+  return m;
+}
+__device__ __forceinline__ void mv_pred16(const MvCtx& m, int& px, int& py) {
+  if (!m.okB && !m.okC && m.okA) { px = m.ax; py = m.ay; return; }
+  const int cnt = (int)m.okA + (int)m.okB + (int)m.okC;
+  if (cnt == 1) { px = m.okA ? m.ax : m.okB ? m.bx : m.cx; py = m.okA ? m.ay : m.okB ? m.by : m.cy; return; }
+  px = median3(m.ax, m.bx, m.cx); py = median3(m.ay, m.by, m.cy);
+}
+__device__ __forceinline__ void mv_pred_skip(const MvCtx& m, int& px, int& py) {
+  px = py = 0;
+  if (!m.okA || !m.okB) return;
+  if ((m.ax == 0 && m.ay == 0) || (m.bx == 0 && m.by == 0)) return;
+  mv_pred16(m, px, py);
+}
+
+// ------------------------------------------------------------------------------------------------ k_cavlc_mb
+constexpr int CAVLC_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
+  __shared__ __align__(16) uint32_t s_words[CAVLC_WARPS][MB_WORDS];
+  __shared__ __align__(16) int16_t s_lv[CAVLC_WARPS][32][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mb = blockIdx.x * CAVLC_WARPS + warp;
+  if (mb >= f.mbw * f.mbh) return;
+  const int mbx = mb % f.mbw, mby = mb / f.mbw;
+  const MbInfo mi = f.mbinfo[mb];
+  uint32_t* words = s_words[warp];
+#pragma unroll
+  for (int i = lane; i < MB_WORDS; i += 32) words[i] = 0;
+
+  // ---- macroblock header fields ---------------------------------------------------------------------
+  const int cbp_l = mi.cbp & 15, cbp_c = mi.cbp >> 4;
+  bool skip = false;
+  int mvdx = 0, mvdy = 0;
+  if (!f.idr) {
+    const MvCtx mc = mv_ctx(f, mbx, mby);
+    int sx, sy, px, py;
+    mv_pred_skip(mc, sx, sy);
+    skip = mi.type == MB_P16 && mi.cbp == 0 && mi.mvx == sx && mi.mvy == sy;
+    mv_pred16(mc, px, py);
+    mvdx = mi.mvx - px; mvdy = mi.mvy - py;
+  }
+  if (skip) {                                    // P_Skip: no bits; k_slice_bits folds it into mb_skip_run
+    if (lane == 0) f.mb_nbits[mb] = 0x80000000u;
+    return;
+  }
+  // ---- which block does this lane code, and with which nC ---------------------------------------------
+  // lane 0: Intra16x16 DC | 1..16: luma blkIdx lane-1 | 17,18: chroma DC | 19..26: chroma AC
+  const uint8_t* nz_own = f.nnz + (size_t)mb * 32;
+  const bool availA = mbx > 0, availB = top_in_slice(f, mby);
+  const uint8_t* nz_a = f.nnz + (size_t)(mb - 1) * 32;
+  const uint8_t* nz_b = f.nnz + (size_t)(mb - f.mbw) * 32;
+  bool coded = false; int start = 0, maxc = 16, nC = 0, cblk = lane;
+  if (lane == 0) { coded = mi.type == MB_I16; }
+  else if (lane <= 16) { coded = (cbp_l >> ((lane - 1) >> 2)) & 1; if (mi.type == MB_I16) { start = 1; maxc = 15; } }
+  else if (lane <= 18) { coded = cbp_c != 0; maxc = 4; nC = -1; }
+  else if (lane <= 26) { coded = cbp_c == 2; start = 1; maxc = 15; }
+  if (coded && nC == 0) {
+    int na = 0, nb = 0; bool oka, okb;
+    if (lane <= 16) {
+      const int b = lane == 0 ? 0 : lane - 1, bx = blk_x[b], by = blk_y[b];
+      oka = bx > 0 || availA; okb = by > 0 || availB;
+      if (bx > 0) na = nz_own[by * 4 + bx - 1]; else if (availA) na = nz_a[by * 4 + 3];
+      if (by > 0) nb = nz_own[(by - 1) * 4 + bx]; else if (availB) nb = nz_b[12 + bx];
+    } else {
+      const int c = (lane - 19) >> 2, b = (lane - 19) & 3, bx = b & 1, by = b >> 1;
+      oka = bx > 0 || availA; okb = by > 0 || availB;
+      if (bx > 0) na = nz_own[16 + c * 4 + by * 2]; else if (availA) na = nz_a[16 + c * 4 + by * 2 + 1];
+      if (by > 0) nb = nz_own[16 + c * 4 + bx]; else if (availB) nb = nz_b[16 + c * 4 + 2 + bx];
+    }
+    nC = oka && okb ? (na + nb + 1) >> 1 : oka ? na : okb ? nb : 0;
+  }
+  // stage this lane's 16 levels in shared memory (dynamic indexing without local memory)
+  if (lane < COEF_BLOCKS) {
+    const uint4* src = reinterpret_cast<const uint4*>(f.coef + ((size_t)mb * COEF_BLOCKS + cblk) * 16);
+    uint4* dst = reinterpret_cast<uint4*>(&s_lv[warp][lane][0]);
+    if (coded) { dst[0] = src[0]; dst[1] = src[1]; }
+  }
+  __syncwarp();
+  const int16_t* lv = &s_lv[warp][lane][start];
+
+  // ---- pass 1: sizes ---------------------------------------------------------------------------------
+  CountSink cs;
+  if (coded) cavlc_block(cs, lv, maxc, nC);
+  int hdr_bits;
+  {
+    CountSink h;
+    if (mi.type == MB_I16) {
+      const int tcode = 1 + mi.i16_mode + 4 * cbp_c + (cbp_l ? 12 : 0);
+      put_ue(h, (uint32_t)(f.idr ? tcode : tcode + 5)); put_ue(h, mi.chroma_mode); put_se(h, 0);
+    } else {
+      put_ue(h, 0); put_se(h, mvdx); put_se(h, mvdy); put_ue(h, cbp_to_codenum_inter[mi.cbp]);
+      if (mi.cbp) put_se(h, 0);
+    }
+    hdr_bits = h.n;
+  }
+  int incl = cs.n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+  const int total_bits = hdr_bits + __shfl_sync(FULL, incl, 31);
+  const int my_off = hdr_bits + incl - cs.n;
+
+  // ---- pass 2: write -----------------------------------------------------------------------------------
+  if (lane == 0) {
+    SmemSink h{words, 0, MB_WORDS * 32};
+    if (mi.type == MB_I16) {
+      const int tcode = 1 + mi.i16_mode + 4 * cbp_c + (cbp_l ? 12 : 0);
+      put_ue(h, (uint32_t)(f.idr ? tcode : tcode + 5)); put_ue(h, mi.chroma_mode); put_se(h, 0);
+    } else {
+      put_ue(h, 0); put_se(h, mvdx); put_se(h, mvdy); put_ue(h, cbp_to_codenum_inter[mi.cbp]);
+      if (mi.cbp) put_se(h, 0);
+    }
+  }
+  if (coded) { SmemSink ws{words, my_off, MB_WORDS * 32}; cavlc_block(ws, lv, maxc, nC); }
+  __syncwarp();
+  int nb = total_bits;
+  if (nb > MB_WORDS * 32) { nb = MB_WORDS * 32; if (lane == 0) atomicExch(f.overflow, 1); }
+  uint32_t* dst = f.mb_words + (size_t)mb * MB_WORDS;
+  for (int i = lane; i < (nb + 31) >> 5; i += 32) dst[i] = words[i];
+  if (lane == 0) f.mb_nbits[mb] = (uint32_t)nb;
+}
+
+// ------------------------------------------------------------------------------------------------ slice header (7.3.3)
+template <class S>
+__device__ __forceinline__ void slice_header(S& s, const FrameCtx& f, int first_mb, int qp) {
+  put_ue(s, (uint32_t)first_mb);
+  put_ue(s, f.idr ? 7u : 5u);
+  put_ue(s, 0);
+  s.put(8, (uint32_t)(f.frame_num & 255));
+  if (f.idr) put_ue(s, (uint32_t)(f.idr_pic_id & 15));
+  if (!f.idr) { s.put(1, 0); s.put(1, 0); }
+  if (f.idr) { s.put(1, 0); s.put(1, 0); } else s.put(1, 0);
+  put_se(s, qp - 26);
+  put_ue(s, 1);
+}
+
+struct GlobalSink {         // same layout as SmemSink, on the slice's RBSP words in HBM
+  uint32_t* w; long long pos;
+  __device__ __forceinline__ void put(int len, uint32_t v) {
+    if (len == 0) return;
+    const long long wi = pos >> 5; const int o = (int)(pos & 31), space = 32 - o;
+    if (len <= space) atomicOr(&w[wi], v << (space - len));
+    else { atomicOr(&w[wi], v >> (len - space)); atomicOr(&w[wi + 1], v << (32 - (len - space))); }
+    pos += len;
+  }
+};
+
+constexpr int SLICE_THREADS = 256;
+
+__device__ __forceinline__ uint32_t rbsp_byte(const uint32_t* w, long long i) { return (__ldcg(&w[i >> 2]) >> (24 - 8 * (int)(i & 3))) & 255u; }
+
+__global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
+  __shared__ long long s_off[SLICE_THREADS];
+  __shared__ uint32_t s_nb[SLICE_THREADS];
+  __shared__ int s_run[SLICE_THREADS];
+  __shared__ long long s_warp_sum[SLICE_THREADS / 32];
+  __shared__ int s_warp_max[SLICE_THREADS / 32];
+  __shared__ long long s_carry_bits;
+  __shared__ int s_carry_last;      // index (within the slice) of the last non-skipped macroblock seen so far
+  __shared__ int s_red[SLICE_THREADS / 32];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = s * f.slice_rows, row1 = min(f.mbh, row0 + f.slice_rows);
+  const int mb0 = row0 * f.mbw, n_mb = (row1 - row0) * f.mbw;
+  const int qp = frame_qp(f);
+  uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
+  if (tid == 0) {
+    GlobalSink g{out, 0};
+    slice_header(g, f, mb0, qp);
+    s_carry_bits = g.pos; s_carry_last = -1;
+  }
+  __syncthreads();
+  for (int base = 0; base < n_mb; base += SLICE_THREADS) {
+    const int i = base + tid;
+    uint32_t nbits = 0; bool skip = true;
+    if (i < n_mb) { const uint32_t v = f.mb_nbits[mb0 + i]; skip = (v >> 31) != 0; nbits = v & 0x7fffffffu; }
+    // last non-skipped index strictly before i  (max-scan)
+    int mine = skip ? -1 : i;
+    int incl_max = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl_max, d); if (lane >= d) incl_max = max(incl_max, o); }
+    if (lane == 31) s_warp_max[warp] = incl_max;
+    __syncthreads();
+    int prev_max = s_carry_last;
+    for (int w = 0; w < warp; w++) prev_max = max(prev_max, s_warp_max[w]);
+    int excl_max = __shfl_up_sync(FULL, incl_max, 1);
+    if (lane == 0) excl_max = -1;
+    excl_max = max(excl_max, prev_max);
+    const int run = i - 1 - excl_max;                      // mb_skip_run in front of macroblock i
+    const int pre = (!skip && !f.idr) ? ue_len((uint32_t)run) : 0;
+    long long tot = skip ? 0 : (long long)pre + nbits;
+    long long incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    long long woff = s_carry_bits;
+    for (int w = 0; w < warp; w++) woff += s_warp_sum[w];
+    s_off[tid] = woff + incl - tot;
+    s_nb[tid] = skip ? 0xffffffffu : nbits;
+    s_run[tid] = run;
+    __syncthreads();
+    if (tid == SLICE_THREADS - 1) {
+      long long t = s_carry_bits;
+      for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_warp_sum[w];
+      s_carry_bits = t;
+      int m = s_carry_last;
+      for (int w = 0; w < SLICE_THREADS / 32; w++) m = max(m, s_warp_max[w]);
+      s_carry_last = m;
+    }
+    // each warp copies 32 macroblocks of the chunk, lanes stride over the macroblock's words
+    for (int k = 0; k < 32; k++) {
+      const int j = warp * 32 + k;
+      if (base + j >= n_mb) break;
+      const uint32_t nb = s_nb[j];
+      if (nb == 0xffffffffu) continue;
+      long long pos = s_off[j];
+      if (!f.idr) {
+        if (lane == 0) { GlobalSink g{out, pos}; put_ue(g, (uint32_t)s_run[j]); }
+        pos += ue_len((uint32_t)s_run[j]);
+      }
+      const uint32_t* src = f.mb_words + (size_t)(mb0 + base + j) * MB_WORDS;
+      for (int w = lane; w < (int)((nb + 31) >> 5); w += 32) {
+        const uint32_t v = src[w];
+        if (v) {
+          const long long p = pos + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);
+          if (o == 0) atomicOr(&out[wi], v);
+          else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // trailing mb_skip_run, rbsp_trailing_bits
+  if (tid == 0) {
+    GlobalSink g{out, s_carry_bits};
+    if (!f.idr) { const int run = n_mb - 1 - s_carry_last; if (run > 0) put_ue(g, (uint32_t)run); }
+    f.slice_bits[s] = g.pos;
+    g.put(1, 1);
+    s_carry_bits = g.pos;
+  }
+  __threadfence();
+  __syncthreads();
+  const long long rbsp_bytes = (s_carry_bits + 7) >> 3;
+  // count emulation-prevention bytes (7.4.1): before byte i iff byte<=3 and zero-run before it is even and >= 2
+  int ep = 0;
+  for (long long i = tid; i < rbsp_bytes; i += SLICE_THREADS) {
+    if (rbsp_byte(out, i) <= 3u) {
+      int z = 0;
+      while (i - 1 - z >= 0 && rbsp_byte(out, i - 1 - z) == 0u) z++;
+      if (z >= 2 && (z & 1) == 0) ep++;
+    }
+  }
+  ep = __reduce_add_sync(FULL, ep);
+  if (lane == 0) s_red[warp] = ep;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_red[w];
+    const int start_len = (s == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of the access unit
+    f.slice_rbsp[s] = (uint32_t)rbsp_bytes;
+    f.slice_size[s] = (uint32_t)(start_len + 1 + rbsp_bytes + t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_pack_au
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_CH = 16;      // bytes per thread per round
+
+__device__ __forceinline__ void rc_update_dev(RcState* rc, long long bits, long long target, int idr, int qp_used) {
+  if (target < 1) target = 1;
+  const long long ref = idr ? 4 * target : target;
+  const long long r = bits * 16 / ref;
+  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
+  long long full = rc->fullness + bits - target;
+  if (full < -4 * target) full = -4 * target;
+  if (full > 16 * target) full = 16 * target;
+  if (full > 4 * target && dq < 1) dq = 1;
+  if (full < -2 * target && dq > -1) dq = -1;
+  rc->fullness = full;
+  rc->qp = clip3i(10, 48, qp_used + dq);
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long au_cap) {
+  __shared__ long long s_base;
+  __shared__ int s_wsum[PACK_THREADS / 32];
+  __shared__ int s_carry;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qp = frame_qp(f);
+  // byte offset of this slice's NAL inside the access unit
+  long long part = 0;
+  for (int j = tid; j < s; j += PACK_THREADS) part += f.slice_size[j];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+  __shared__ long long s_part[PACK_THREADS / 32];
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    long long t = f.idr ? f.param_len : 0;
+    for (int w = 0; w < PACK_THREADS / 32; w++) t += s_part[w];
+    s_base = t; s_carry = 0;
+  }
+  __syncthreads();
+  uint8_t* au = f.au + sizeof(AuHeader);
+  const long long cap = au_cap - (long long)sizeof(AuHeader);
+  const long long base = s_base;
+  const uint32_t* in = f.slice_buf + (size_t)s * f.slice_words;
+  const long long n = f.slice_rbsp[s];
+  const int start_len = (s == 0 && !f.idr) ? 4 : 3;
+  if (tid == 0 && base + start_len + 1 <= cap) {
+    long long o = base;
+    if (start_len == 4) au[o++] = 0;
+    au[o++] = 0; au[o++] = 0; au[o++] = 1;
+    au[o++] = (uint8_t)(((f.idr ? 3 : 2) << 5) | (f.idr ? 5 : 1));
+  }
+  const long long out0 = base + start_len + 1;
+  for (long long cb = 0; cb < n; cb += (long long)PACK_THREADS * PACK_CH) {
+    const long long i0 = cb + (long long)tid * PACK_CH;
+    uint32_t bytes[PACK_CH]; uint32_t epmask = 0; int cnt = 0;
+    if (i0 < n) {
+      int z = 0;                                   // zero run in front of the chunk
+      while (i0 - 1 - z >= 0 && rbsp_byte(in, i0 - 1 - z) == 0u) z++;
+#pragma unroll
+      for (int k = 0; k < PACK_CH; k++) {
+        const long long i = i0 + k;
+        const uint32_t b = i < n ? rbsp_byte(in, i) : 0xffu;
+        bytes[k] = b;
+        if (i < n && b <= 3u && z >= 2 && (z & 1) == 0) { epmask |= 1u << k; cnt++; }
+        z = b == 0u ? z + 1 : 0;
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int before = s_carry;
+    for (int w = 0; w < warp; w++) before += s_wsum[w];
+    before += incl - cnt;
+    if (i0 < n) {
+      long long o = out0 + i0 + before;
+#pragma unroll
+      for (int k = 0; k < PACK_CH; k++) {
+        if (i0 + k < n) {
+          if ((epmask >> k) & 1u) { if (o < cap) au[o] = 3; o++; }
+          if (o < cap) au[o] = (uint8_t)bytes[k];
+          o++;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { int t = s_carry; for (int w = 0; w < PACK_THREADS / 32; w++) t += s_wsum[w]; s_carry = t; }
+    __syncthreads();
+  }
+  // self-clean the slice scratch for the next picture (k_slice_bits builds the RBSP with atomicOr)
+  {
+    uint32_t* w = f.slice_buf + (size_t)s * f.slice_words;
+    const long long nw = min((long long)f.slice_words, (n >> 2) + 2);
+    for (long long i = tid; i < nw; i += PACK_THREADS) w[i] = 0;
+  }
+  if (s == 0) {
+    if (f.idr) for (int i = tid; i < f.param_len; i += PACK_THREADS) au[i] = f.param_sets[i];
+    if (tid == 0) {
+      long long total = f.idr ? f.param_len : 0, bits = 0;
+      for (int j = 0; j < f.n_slices; j++) { total += f.slice_size[j]; bits += f.slice_bits[j]; }
+      AuHeader* h = reinterpret_cast<AuHeader*>(f.au);
+      int ovf = *f.overflow;
+      if (total > cap) { ovf |= 2; total = cap; }
+      h->size = (int32_t)total; h->qp = qp; h->is_idr = f.idr; h->n_slices = f.n_slices; h->total_bits = bits;
+      h->overflow = ovf;
+      if (f.rc_mode == 0) rc_update_dev(f.rc, total * 8, f.target_bits, f.idr, qp);
+      h->next_qp = f.rc->qp;
+      f.rc->last_qp = qp; f.rc->frames++;
+    }
+  }
+}
+
+int launch_cavlc(const FrameCtx& f, cudaStream_t st) {
+  const int mbs = f.mbw * f.mbh;
+  k_cavlc_mb<<<(mbs + CAVLC_WARPS - 1) / CAVLC_WARPS, 32 * CAVLC_WARPS, 0, st>>>(f);
+  return 1;
+}
+int launch_slice(const FrameCtx& f, cudaStream_t st) {
+  k_slice_bits<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
+  return 1;
+}
+int launch_pack_cap(const FrameCtx& f, long long au_cap, cudaStream_t st) {
+  k_pack_au<<<f.n_slices, PACK_THREADS, 0, st>>>(f, au_cap);
+  return 1;
+}
+
+}  // namespace b2v

@@ -1,0 +1,163 @@
+// h264_inter.cu — P pictures: one warp per macroblock, P_L0_16x16 (ITU-T H.264 8.4).
+//
+//  1. the 16x16 source block and a 48x48 window of the previous reconstruction (L2-resident: a 4K
+//     NV12 frame is 12.4 MB against 126 MB of L2) are staged in shared memory;
+//  2. exhaustive full-sample search, dx in [-16,15] (one candidate column per LANE), dy in [-16,16]:
+//     every window row is byte-aligned once per lane with funnel shifts and then feeds the 16 (row, dy)
+//     pairs it belongs to — 33 SAD accumulators live in registers, VABSDIFF4.U8.ACC does 4 pixels per
+//     instruction; cost = SAD + lambda*(bits(mvx)+bits(mvy)); the arg-min is a single warp-wide
+//     REDUX.MIN over (cost << 11 | candidate index);
+//  3. prediction (luma copy, chroma 1/8-sample bilinear), residual transform/quantisation and
+//     reconstruction with one lane per 4x4 block (h264_common.cuh).
+// There is no dependency between macroblocks of a P picture: motion-vector prediction and the P_Skip
+// decision only matter for entropy coding and are resolved in h264_entropy.cu.
+// Encoder decisions: DESIGN.md §5.3; CPU restatement: oracle/h264_ref.c encode_inter_mb().
+#include "h264_common.cuh"
+#include "h264_kernels.h"
+
+namespace b2v {
+
+constexpr int WIN_ROWS = 48, WIN_WORDS = 12;
+constexpr int WARPS_PER_BLOCK = 4;
+
+struct InterSm {
+  MbTile t;
+  uint32_t win[WIN_ROWS][WIN_WORDS];
+};
+
+__host__ __device__ constexpr int se_bits_c(int v) {
+  unsigned c = (v > 0 ? 2u * (unsigned)v - 1u : (unsigned)(-2 * v)) + 1u;
+  int len = 0;
+  while ((c >> len) > 1) len++;
+  return 2 * len + 1;
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
+  __shared__ __align__(16) InterSm sm_all[WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mb = blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (mb >= f.mbw * f.mbh) return;
+  InterSm& sm = sm_all[warp];
+  MbTile& t = sm.t;
+  const int mbx = mb % f.mbw, mby = mb / f.mbw, x0 = mbx * 16, y0 = mby * 16;
+  const int qp = frame_qp(f);
+  const size_t ysz = (size_t)f.cw * f.ch;
+  const uint8_t* __restrict__ ref_y = f.ref; const uint8_t* __restrict__ ref_uv = f.ref + ysz;
+  const int r8 = lane >> 1, c8 = (lane & 1) * 8, rc4 = lane >> 2, cc4 = (lane & 3) * 4;
+
+  // ---- stage the source block and the search window ------------------------------------------------
+  {
+    const uint2 v = *reinterpret_cast<const uint2*>(f.cur + (size_t)(y0 + r8) * f.cw + x0 + c8);
+    *reinterpret_cast<uint2*>(&t.cur_y[r8][c8]) = v;
+    if (lane < 16) {
+      const uint2 w = *reinterpret_cast<const uint2*>(f.cur + ysz + (size_t)(mby * 8 + r8) * f.cw + x0 + c8);
+      *reinterpret_cast<uint2*>(&t.cur_uv[r8][c8]) = w;
+    }
+    const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
+    if (x_inside) {
+      for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
+        const int row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        const int y = clip3i(0, f.ch - 1, y0 - 16 + row);
+        sm.win[row][w] = __ldg(reinterpret_cast<const uint32_t*>(ref_y + (size_t)y * f.cw + x0 - 16) + w);
+      }
+    } else {   // picture edge: per-sample clamping (8.4.2.2.1 reference sample padding)
+      for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
+        const int row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        const uint8_t* rr = ref_y + (size_t)clip3i(0, f.ch - 1, y0 - 16 + row) * f.cw;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rr + clip3i(0, f.cw - 1, x0 - 16 + w * 4 + k)) << (8 * k);
+        sm.win[row][w] = v;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- exhaustive search ---------------------------------------------------------------------------
+  uint32_t c[16][4];
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    const uint4 v = *reinterpret_cast<const uint4*>(&t.cur_y[r][0]);
+    c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
+  }
+  uint32_t acc[33];
+#pragma unroll
+  for (int i = 0; i < 33; i++) acc[i] = 0;
+  const int wi = lane >> 2, sh = (lane & 3) * 8;
+#pragma unroll
+  for (int y = 0; y < WIN_ROWS; y++) {
+    const uint32_t* wr = sm.win[y] + wi;
+    const uint32_t w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3], w4 = wr[4];
+    const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      const int dyi = y - r;
+      if (dyi >= 0 && dyi <= 32)
+        acc[dyi] = __vsadu4(c[r][0], a0) + (__vsadu4(c[r][1], a1) + (__vsadu4(c[r][2], a2) + (__vsadu4(c[r][3], a3) + acc[dyi])));
+    }
+  }
+  const int lambda = me_lambda[qp];
+  const int bits_x = se_bits_c(4 * (lane - 16));
+  uint32_t best = 0xffffffffu;
+#pragma unroll
+  for (int dyi = 0; dyi <= 32; dyi++) {
+    const uint32_t cost = acc[dyi] + (uint32_t)(lambda * (bits_x + se_bits_c(4 * (dyi - 16))));
+    const uint32_t key = (cost << 11) | (uint32_t)(dyi * 32 + lane);
+    best = min(best, key);
+  }
+  best = __reduce_min_sync(FULL, best);
+  const int dyi = (best & 2047) >> 5, dxi = best & 31, dx = dxi - 16, dy = dyi - 16;
+
+  // ---- prediction ------------------------------------------------------------------------------------
+  {
+    const uint8_t* wb = reinterpret_cast<const uint8_t*>(&sm.win[dyi + r8][0]) + dxi + c8;
+    uint32_t p0 = 0, p1 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { p0 |= (uint32_t)wb[j] << (8 * j); p1 |= (uint32_t)wb[4 + j] << (8 * j); }
+    *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = p0;
+    *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = p1;
+    // chroma: mvC = (4dx, 4dy) in 1/8 chroma samples (8.4.1.4, 8.4.2.2.2)
+    const int xi = dx >> 1, yi = dy >> 1, xf = (dx & 1) * 4, yf = (dy & 1) * 4;
+    const int cwc = f.cw >> 1, chc = f.ch >> 1;
+    const int ya = clip3i(0, chc - 1, mby * 8 + yi + rc4), yb = clip3i(0, chc - 1, mby * 8 + yi + rc4 + 1);
+    uint32_t out = 0;
+#pragma unroll
+    for (int px = 0; px < 2; px++) {
+      const int x = (lane & 3) * 2 + px;
+      const int xa = clip3i(0, cwc - 1, mbx * 8 + xi + x), xb = clip3i(0, cwc - 1, mbx * 8 + xi + x + 1);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int A = __ldg(ref_uv + (size_t)ya * f.cw + xa * 2 + k), B = __ldg(ref_uv + (size_t)ya * f.cw + xb * 2 + k);
+        const int C = __ldg(ref_uv + (size_t)yb * f.cw + xa * 2 + k), D = __ldg(ref_uv + (size_t)yb * f.cw + xb * 2 + k);
+        const int v = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
+        out |= (uint32_t)v << (8 * (px * 2 + k));
+      }
+    }
+    *reinterpret_cast<uint32_t*>(&t.pred_uv[rc4][cc4]) = out;
+  }
+  __syncwarp();
+
+  // ---- residual + reconstruction ------------------------------------------------------------------------
+  const int cbp = transform_mb<false>(t, lane, qp, f.coef + (size_t)mb * COEF_BLOCKS * 16, f.nnz + (size_t)mb * 32);
+  __syncwarp();
+  {
+    const uint2 v = *reinterpret_cast<const uint2*>(&t.rec_y[r8][c8]);
+    *reinterpret_cast<uint2*>(f.recon + (size_t)(y0 + r8) * f.cw + x0 + c8) = v;
+    if (lane < 16) {
+      const uint2 w = *reinterpret_cast<const uint2*>(&t.rec_uv[r8][c8]);
+      *reinterpret_cast<uint2*>(f.recon + ysz + (size_t)(mby * 8 + r8) * f.cw + x0 + c8) = w;
+    }
+    if (lane == 0) {
+      MbInfo mi; mi.mvx = (int16_t)(4 * dx); mi.mvy = (int16_t)(4 * dy); mi.type = MB_P16; mi.i16_mode = 0; mi.chroma_mode = 0; mi.cbp = (uint8_t)cbp;
+      f.mbinfo[mb] = mi;
+    }
+  }
+}
+
+int launch_inter(const FrameCtx& f, cudaStream_t st) {
+  const int mbs = f.mbw * f.mbh;
+  k_inter_mb<<<(mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0, st>>>(f);
+  return 1;
+}
+
+}  // namespace b2v

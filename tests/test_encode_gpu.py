@@ -1,0 +1,121 @@
+"""GPU parity: the CUDA H.264 encoder vs oracle/h264_ref.c — access units and reconstruction bit-exact,
+through the C-ABI (ring ingest -> fused CSC -> encode -> callback)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import avdec
+from selkies_b200 import _native as N
+from selkies_b200.session import Session
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def encode_both(w, h, frames, *, qp=28, slice_rows=1, idr_at=(0,), rc_mode=N.B2V_RC_CQP, kbps=0, fps=30.0):
+    enc = oracle.RefEncoder(w, h, slice_rows)
+    target = int(kbps * 1000 / fps) if kbps else 0
+    ref_aus, ref_rec = [], []
+    with Session(w, h, rc_mode=rc_mode, crf=qp, bitrate_kbps=kbps or 8000, fps=fps, slice_rows=slice_rows, gop=-1) as s:
+        for i, f in enumerate(frames):
+            if i in idr_at and i > 0:
+                s.flush()
+                s.request_idr()
+            s.submit(f)
+        s.flush()
+        got = s.take_frames()
+        gy, guv = s.recon()
+    for i, f in enumerate(frames):
+        ref_aus.append(enc.encode_bgra(f, i in idr_at, rc_mode=1 if rc_mode == N.B2V_RC_CQP else 0, qp=qp, target_bits=target))
+    ry, ruv = enc.recon()
+    return got, ref_aus, (gy, guv), (ry, ruv)
+
+
+def assert_same(got, ref_aus, grec, rrec):
+    assert len(got) == len(ref_aus)
+    for i, (g, r) in enumerate(zip(got, ref_aus)):
+        assert g.frame_id == i
+        if g.data != r:
+            n = min(len(g.data), len(r))
+            first = next((k for k in range(n) if g.data[k] != r[k]), n)
+            raise AssertionError(f"frame {i}: AU differs at byte {first} (gpu {len(g.data)} B, oracle {len(r)} B)")
+    assert np.array_equal(grec[0], rrec[0]) and np.array_equal(grec[1], rrec[1])
+
+
+@pytest.mark.parametrize("w,h", [(16, 16), (64, 48), (130, 70), (320, 192)])
+@pytest.mark.parametrize("qp", [12, 28, 44])
+def test_intra_bit_exact(w, h, qp):
+    frames = [synth.noise(w, h, 3), synth.desktop(w, h, 1)]
+    got, ref, grec, rrec = encode_both(w, h, frames, qp=qp, idr_at=(0, 1))
+    assert_same(got, ref, grec, rrec)
+    assert all(g.is_key for g in got)
+
+
+@pytest.mark.parametrize("w,h,slice_rows", [(64, 48, 1), (160, 96, 1), (160, 96, 2), (320, 192, 3), (130, 70, 100)])
+def test_p_frames_bit_exact(w, h, slice_rows):
+    frames = [synth.desktop(w, h, t) for t in range(5)]
+    got, ref, grec, rrec = encode_both(w, h, frames, qp=30, slice_rows=slice_rows)
+    assert_same(got, ref, grec, rrec)
+    assert [g.is_key for g in got] == [True, False, False, False, False]
+
+
+def test_motion_and_noise_bit_exact():
+    base = synth.noise(256, 128, 9)
+    frames = [np.roll(base, (3 * t, -5 * t), axis=(0, 1)) for t in range(4)]
+    assert_same(*encode_both(256, 128, frames, qp=26))
+    frames = [synth.bars(192, 112, t) for t in range(6)]
+    assert_same(*encode_both(192, 112, frames, qp=22, slice_rows=2))
+
+
+def test_static_scene_is_skipped():
+    f = synth.desktop(320, 192, 0)
+    got, ref, grec, rrec = encode_both(320, 192, [f, f, f], qp=30)
+    assert_same(got, ref, grec, rrec)
+    assert len(got[2].data) < 150
+
+
+def test_cbr_rate_control_bit_exact():
+    w, h = 320, 192
+    frames = [synth.desktop(w, h, t) for t in range(12)]
+    got, ref, grec, rrec = encode_both(w, h, frames, rc_mode=N.B2V_RC_CBR, kbps=600, fps=30.0)
+    assert_same(got, ref, grec, rrec)
+    assert len({g.qp for g in got}) > 1          # the controller actually moved
+
+
+def test_gpu_stream_decodes_to_its_reconstruction():
+    w, h = 320, 184                               # cropped height
+    frames = [synth.desktop(w, h, t) for t in range(4)]
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=27) as s:
+        recs = []
+        for f in frames:
+            s.submit(f)
+            s.flush()
+            recs.append(s.recon())
+        got = s.take_frames()
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert len(dec) == len(frames)
+    for (Y, U, V), (ry, ruv) in zip(dec, recs):
+        assert np.array_equal(Y, ry[:h, :w]) and np.array_equal(U, ruv[: h // 2, 0:w:2]) and np.array_equal(V, ruv[: h // 2, 1:w:2])
+    sy, _ = oracle.csc_nv12(frames[-1])
+    assert avdec.psnr(dec[-1][0], sy) > 33.0
+
+
+def test_1080p_one_idr_one_p_bit_exact():
+    """BASELINE config 1 size (coded 1920x1088, bottom crop 8)."""
+    w, h = 1920, 1080
+    frames = [synth.desktop(w, h, 0), synth.desktop(w, h, 1)]
+    assert_same(*encode_both(w, h, frames, qp=30))
+
+
+def test_pixelflux_header_mode():
+    w, h = 64, 48
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=30, header_mode=N.B2V_HDR_PIXELFLUX) as s:
+        s.submit(synth.noise(w, h, 1))
+        s.submit(synth.noise(w, h, 2))
+        s.flush()
+        got = s.take_frames()
+    for i, g in enumerate(got):
+        d = g.data
+        assert d[0] == 0x04 and d[1] == (1 if i == 0 else 0)
+        assert int.from_bytes(d[2:4], "big") == i and int.from_bytes(d[6:8], "big") == w and int.from_bytes(d[8:10], "big") == h
+        assert d[10:14] == b"\x00\x00\x00\x01"
