@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native video hot path (driver contract).
+
+Workload (BASELINE.json metric "4K frames/sec encoded per GPU", configs[2]): synthetic desktop-like
+3840x2160 BGRA frames -> fused BT.709 CSC -> H.264 Constrained-Baseline (one IDR, then P pictures with
+the exhaustive warp-SAD motion search), CBR 20 Mbit/s @ 60 fps nominal, free-running.
+A STEP is one batch of FRAMES_PER_STEP frames through one session (one session per GPU).
+
+  value  frames/s with the BGRA inputs already resident in HBM (b2v_submit_resident), device-timed
+  e2e    frames/s through the host-buffer API: pinned host ring -> cudaMemcpyAsync H2D -> CSC -> encode
+         -> D2H of every access unit -> Python callback, wall-clock + device timer inside the timed region
+  roofline       the fused CSC kernel: algorithmic bytes (5.5 B/px) / CUDA-event time per launch, in-step
+  cpu_baseline   the CPU restatement (oracle/) on the host cores, bounded sample (rank 0, N=1 only)
+
+`--impl reference` times the CPU path only (the reference's own videoconvert+x264enc pipeline cannot
+run here — SURVEY.md §8c — so the arm runs the oracle port, all host threads, labelled kind="port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 3840, 2160
+FPS_NOMINAL = 60.0
+BITRATE_KBPS = 20000
+FRAMES_PER_STEP = 16
+N_DISTINCT = 8            # distinct input frames cycled: 8 x 33.2 MB = 265 MB > 126 MB of L2
+ALG_BYTES_PER_PX = 5.5    # 4 B BGRA read + 1 B Y + 0.5 B CbCr written
+
+
+def synth_frames(n, w=W, h=H):
+    from tests import synth
+    return [synth.desktop(w, h, t) for t in range(n)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_sample(frames, n_p: int, threads: int | None = None):
+    """Oracle CSC + encode of 1 IDR + n_p P pictures on the host cores; returns (P frames/s, seconds, threads)."""
+    import oracle
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    enc = oracle.RefEncoder(W, H)
+    target = int(BITRATE_KBPS * 1000 / FPS_NOMINAL)
+    enc.encode_bgra(frames[0], True, rc_mode=0, target_bits=target)
+    t0 = time.perf_counter()
+    for i in range(n_p):
+        enc.encode_bgra(frames[(i + 1) % len(frames)], False, rc_mode=0, target_bits=target)
+    dt = time.perf_counter() - t0
+    return n_p / dt, dt, (threads or os.cpu_count())
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on all host threads; a step = 1 P picture of the same workload."""
+    if rank != 0:
+        return
+    frames = synth_frames(min(N_DISTINCT, 4))
+    import oracle
+    enc = oracle.RefEncoder(W, H)
+    target = int(BITRATE_KBPS * 1000 / FPS_NOMINAL)
+    enc.encode_bgra(frames[0], True, rc_mode=0, target_bits=target)
+    for i in range(args.warmup):
+        enc.encode_bgra(frames[(i + 1) % len(frames)], False, rc_mode=0, target_bits=target)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        enc.encode_bgra(frames[(i + 1 + args.warmup) % len(frames)], False, rc_mode=0, target_bits=target)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "4K frames/sec encoded", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} P pictures 3840x2160 (CSC + encode), OpenMP over macroblock rows; "
+                                   "the reference's videoconvert+x264enc is absent from this image"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(frames_per_step):
+    return {"workload": "C2: 3840x2160 synthetic desktop BGRA -> fused BT.709 CSC -> H.264 CBP (IDR then P, full-pel exhaustive ME +-16, CAVLC)",
+            "frames_per_step": frames_per_step, "rate_control": f"CBR {BITRATE_KBPS} kbit/s @ {FPS_NOMINAL:g} fps nominal, free-running",
+            "slice_rows": 1, "sessions_per_gpu": 1,
+            "l2_policy": f"inputs larger than L2: {N_DISTINCT} distinct frames x 33.2 MB cycled", "parallelism": "one independent session per GPU (no collective)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from selkies_b200 import _native as N
+    from selkies_b200.session import Session
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    frames = synth_frames(N_DISTINCT)
+    peak, peak_src = measured_peak()
+    flags = N.B2V_FLAG_TIMING
+    sess = Session(W, H, fps=FPS_NOMINAL, device=local_rank, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS,
+                   ring_slots=N_DISTINCT, flags=flags, collect=False)
+    out_bytes = [0]
+
+    def on_frame(fptr):
+        out_bytes[0] += fptr.contents.size
+    sess._on_frame = on_frame
+
+    # ---------------- leg 1: inputs resident in HBM ----------------------------------------------------
+    for i, f in enumerate(frames):
+        sess.resident_upload(i, f)
+
+    def step_resident(k0):
+        for j in range(FRAMES_PER_STEP):
+            sess.submit_resident((k0 + j) % N_DISTINCT)
+
+    k = 0
+    for _ in range(args.warmup):
+        step_resident(k); k += FRAMES_PER_STEP
+    sess.flush()
+    sess.reset_stats()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    sess.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident(k); k += FRAMES_PER_STEP
+    dev_ms = sess.timer_stop()
+    wall_ms = 1000 * (time.perf_counter() - t0)
+    barrier()
+    st = sess.stats()
+    n_frames = args.steps * FRAMES_PER_STEP
+    t_ms = max_over_ranks(max(dev_ms, 0.0))
+    value = sum_over_ranks(float(n_frames)) / (t_ms / 1000.0)
+
+    # ---------------- leg 2: end to end from pinned host buffers -----------------------------------------
+    # pre-fill the pinned ring once (the producer — XShm grab in the reference — writes into these slots);
+    # every frame is then copied H2D inside the timed region and every access unit copied back D2H.
+    for i in range(N_DISTINCT):
+        slot, view = sess.acquire()
+        view[...] = frames[i]
+        sess.submit_slot(slot)
+    sess.flush()
+
+    def step_host():
+        for _ in range(FRAMES_PER_STEP):
+            slot, _view = sess.acquire()       # round-robin: slot i still holds distinct frame i
+            sess.submit_slot(slot)
+
+    for _ in range(args.warmup):
+        step_host()
+    sess.flush()
+    st0 = sess.stats()
+    out_bytes[0] = 0
+    barrier()
+    sess.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    e2e_dev_ms = sess.timer_stop()
+    e2e_wall_ms = 1000 * (time.perf_counter() - t0)
+    barrier()
+    clk = clocks.stop()
+    st1 = sess.stats()
+    e2e_ms = max_over_ranks(max(e2e_wall_ms, e2e_dev_ms))
+    e2e_value = sum_over_ranks(float(n_frames)) / (e2e_ms / 1000.0)
+    h2d_step = (st1["h2d_bytes"] - st0["h2d_bytes"]) / args.steps
+    d2h_step = (st1["d2h_bytes"] - st0["d2h_bytes"]) / args.steps
+
+    # ---------------- roofline of the fused CSC kernel (in-step CUDA-event pairs) -------------------------
+    alg = W * H * ALG_BYTES_PER_PX
+    csc_ms = st["ms_csc"] / max(1, st["n_csc"])
+    achieved = alg / (csc_ms * 1e-3) / 1e9 if csc_ms > 0 else 0.0
+    burst_ms = sess.bench_csc_burst(N_DISTINCT, 200)
+    roofline = {"bound": "hbm", "kernel": "csc_bgra_nv12_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": alg, "us_per_launch": csc_ms * 1e3,
+                "frac_of_8TBps_nominal": achieved / 8000.0,
+                "burst": {"note": "200 back-to-back launches between one event pair, same 8 cycled frames",
+                          "us_per_launch": burst_ms * 1e3, "achieved": alg / (burst_ms * 1e-3) / 1e9,
+                          "frac": alg / (burst_ms * 1e-3) / 1e9 / peak}}
+    kern = {k: (st["ms_" + k] / max(1, st["n_" + k])) * 1e3 for k in ("csc", "intra", "inter", "cavlc", "slice", "pack")}
+    kern["gpu_span_per_frame"] = st["ms_total_gpu"] / max(1, st["n_csc"]) * 1e3
+    sess.close()
+
+    # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            one_fps, one_dt, _ = cpu_sample(frames, 2, threads=1)
+            all_fps, all_dt, cores = cpu_sample(frames, 8, threads=None)
+            cpu = {"value": all_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "1 IDR + 8 P pictures 3840x2160 (oracle CSC + encode, OpenMP over macroblock rows), IDR untimed; "
+                             f"1 thread: {one_fps:.3f} frames/s over 2 P pictures",
+                   "single_thread_value": one_fps,
+                   "note": "CPU restatement of this repo's encoder, not x264/videoconvert (absent from the image)"}
+        except Exception as e:  # the checker failing must not hide the GPU number
+            cpu = {"value": None, "error": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "4K frames/sec encoded", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(FRAMES_PER_STEP),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                    "wall_ms": e2e_wall_ms, "device_ms": e2e_dev_ms, "access_unit_bytes_per_frame": out_bytes[0] / max(1, n_frames)},
+            "gpu_launches": int(st["kernel_launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "kernels_us": kern, "wall_ms_resident": wall_ms, "target_fps": 240,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

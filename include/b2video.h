@@ -136,6 +136,12 @@ int  b2v_get_recon(void* h, void* nv12_host);
 /* repeat the CSC kernel `iters` times over resident frames and return mean ms per launch
  * (CUDA events on the launching stream); used by bench.py for the roofline leg. */
 int  b2v_bench_csc(void* h, int32_t n_resident, int32_t iters, float* ms_per_launch);
+/* same, but `iters` launches back to back between ONE event pair (amortises the event/launch gap) */
+int  b2v_bench_csc_burst(void* h, int32_t n_resident, int32_t iters, float* ms_per_launch);
+/* device-side stopwatch on the encode stream: start = after everything submitted so far has drained;
+ * stop = after every frame submitted since has been delivered.  bench.py times its K steps with it. */
+int  b2v_timer_start(void* h);
+int  b2v_timer_stop(void* h, float* ms);
 const char* b2v_last_error(void);
 
 #ifdef __cplusplus

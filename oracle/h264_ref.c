@@ -405,12 +405,19 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   const uint8_t* refy = plane_y(e, e->cur ^ 1); const uint8_t* refuv = plane_uv(e, e->cur ^ 1);
   int x0 = mbx * 16, y0 = mby * 16, lambda = me_lambda[qp];
   uint32_t best = 0xffffffffu; int bdx = 0, bdy = 0;
+  /* reference samples the search can touch, with picture-edge clamping (8.4.2.2.1): win[j][i] = ref(x0-16+i, y0-16+j) */
+  uint8_t win[48][48];
+  for (int j = 0; j < 48; j++) {
+    const uint8_t* rr = refy + (size_t)clip3(0, e->ch - 1, y0 - 16 + j) * e->cw;
+    if (x0 >= 16 && x0 + 32 <= e->cw) memcpy(win[j], rr + x0 - 16, 48);
+    else for (int i = 0; i < 48; i++) win[j][i] = rr[clip3(0, e->cw - 1, x0 - 16 + i)];
+  }
   for (int dy = -16; dy <= 16; dy++)
     for (int dx = -16; dx <= 15; dx++) {
       int sad = 0;
       for (int r = 0; r < 16; r++) {
-        const uint8_t* rr = refy + (size_t)clip3(0, e->ch - 1, y0 + dy + r) * e->cw;
-        for (int c = 0; c < 16; c++) sad += iabs(cy[r * 16 + c] - rr[clip3(0, e->cw - 1, x0 + dx + c)]);
+        const uint8_t* rr = &win[dy + 16 + r][dx + 16];
+        for (int c = 0; c < 16; c++) sad += iabs(cy[r * 16 + c] - rr[c]);
       }
       uint32_t cost = (uint32_t)(sad + lambda * (se_bits(4 * dx) + se_bits(4 * dy)));
       uint32_t key = (cost << 11) | (uint32_t)((dy + 16) * 32 + (dx + 16));

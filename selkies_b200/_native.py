@@ -76,6 +76,9 @@ SYMBOLS = [
     ("b2v_csc_nv12", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ("b2v_get_recon", C.c_int, [C.c_void_p, C.c_void_p]),
     ("b2v_bench_csc", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    ("b2v_bench_csc_burst", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    ("b2v_timer_start", C.c_int, [C.c_void_p]),
+    ("b2v_timer_stop", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("b2v_last_error", C.c_char_p, []),
 ]
 

@@ -75,6 +75,8 @@ struct Session {
   bool out_free[kMaxSlots] = {};
   size_t au_cap = 0;
   int out_next = 0;
+  int ring_next = 0;
+  cudaEvent_t ev_timer[2] = {};
 
   // frame sequencing
   uint32_t frame_id = 0;
@@ -348,6 +350,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
     cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
   }
   for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventCreate(&s->ev_t[i][k]);
+  cudaEventCreate(&s->ev_timer[0]); cudaEventCreate(&s->ev_timer[1]);
   int rc = alloc_geometry(s);
   if (rc) { free_geometry(s); delete s; return rc; }
   s->out_thread = std::thread(output_loop, s);
@@ -373,6 +376,7 @@ void b2v_destroy(void* h) {
     cudaEventDestroy(s->ev_enc[i]); cudaEventDestroy(s->ev_out[i]);
   }
   for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventDestroy(s->ev_t[i][k]);
+  cudaEventDestroy(s->ev_timer[0]); cudaEventDestroy(s->ev_timer[1]);
   cudaStreamDestroy(s->st_copy); cudaStreamDestroy(s->st_enc); cudaStreamDestroy(s->st_out);
   delete s;
 }
@@ -381,13 +385,11 @@ void* b2v_ring_acquire(void* h, int32_t* slot) {
   Session* s = (Session*)h;
   if (!s || !slot) { fail(B2V_EINVAL, "null argument"); return nullptr; }
   std::unique_lock<std::mutex> lk(s->mu);
-  int found = -1;
-  s->cv_slot.wait(lk, [&] {
-    if (s->stopping) return true;
-    for (int i = 0; i < s->n_slots; i++) if (s->slot_free[i]) { found = i; return true; }
-    return false;
-  });
-  if (found < 0) { fail(B2V_ESTATE, "session is stopping"); return nullptr; }
+  const int want = s->ring_next;                    // strict round-robin: slot k is reused every n_slots frames
+  s->cv_slot.wait(lk, [&] { return s->stopping || s->slot_free[want]; });
+  if (s->stopping) { fail(B2V_ESTATE, "session is stopping"); return nullptr; }
+  const int found = want;
+  s->ring_next = (want + 1) % s->n_slots;
   s->slot_free[found] = false;
   *slot = found;
   return s->host_slot[found];
@@ -484,7 +486,7 @@ int b2v_set_resolution(void* h, int32_t sw, int32_t sh, int32_t dw, int32_t dh) 
   rc = alloc_geometry(s);
   std::lock_guard<std::mutex> lk(s->mu);
   s->want_idr = true;            // new SPS/PPS + IDR
-  s->out_next = 0;
+  s->out_next = 0; s->ring_next = 0;
   return rc;
 }
 
@@ -579,6 +581,56 @@ int b2v_bench_csc(void* h, int32_t n_resident, int32_t iters, float* ms_per_laun
   for (auto o : outs) cudaFree(o);
   CK(cudaGetLastError());
   *ms_per_launch = (float)(total / iters);
+  return 0;
+}
+
+int b2v_timer_start(void* h) {
+  Session* s = (Session*)h;
+  if (!s) return fail(B2V_EINVAL, "null handle");
+  int rc = b2v_flush(h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(s->ev_timer[0], s->st_enc));
+  return 0;
+}
+
+int b2v_timer_stop(void* h, float* ms) {
+  Session* s = (Session*)h;
+  if (!s || !ms) return fail(B2V_EINVAL, "null argument");
+  int rc = b2v_flush(h);            // every callback delivered (D2H of the last access unit included)
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  CK(cudaEventRecord(s->ev_timer[1], s->st_enc));
+  CK(cudaEventSynchronize(s->ev_timer[1]));
+  CK(cudaEventElapsedTime(ms, s->ev_timer[0], s->ev_timer[1]));
+  return 0;
+}
+
+int b2v_bench_csc_burst(void* h, int32_t n_resident, int32_t iters, float* ms_per_launch) {
+  Session* s = (Session*)h;
+  if (!s || n_resident <= 0 || n_resident > (int)s->resident.size() || iters <= 0 || !ms_per_launch) return fail(B2V_EINVAL, "bad argument");
+  int rc = b2v_flush(h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> sub(s->submit_mu);
+  CK(cudaSetDevice(s->device));
+  std::vector<uint8_t*> outs(n_resident, nullptr);
+  size_t ob = (size_t)s->coded_w * s->coded_h * 3 / 2;
+  for (auto& o : outs) CK(cudaMalloc((void**)&o, ob));
+  for (int i = 0; i < n_resident; i++) launch_csc(csc_params(s, s->resident[i], s->src_w * 4, outs[i]), s->sm_count, s->st_enc);
+  CK(cudaStreamSynchronize(s->st_enc));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, s->st_enc);
+  for (int i = 0; i < iters; i++) { int k = i % n_resident; launch_csc(csc_params(s, s->resident[k], s->src_w * 4, outs[k]), s->sm_count, s->st_enc); }
+  cudaEventRecord(e1, s->st_enc);
+  CK(cudaStreamSynchronize(s->st_enc));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (auto o : outs) cudaFree(o);
+  CK(cudaGetLastError());
+  *ms_per_launch = ms / iters;
   return 0;
 }
 

@@ -144,6 +144,19 @@ class Session:
         N.check(self._lib.b2v_bench_csc(self._h, n_resident, iters, C.byref(ms)))
         return float(ms.value)
 
+    def bench_csc_burst(self, n_resident: int, iters: int) -> float:
+        ms = C.c_float()
+        N.check(self._lib.b2v_bench_csc_burst(self._h, n_resident, iters, C.byref(ms)))
+        return float(ms.value)
+
+    def timer_start(self) -> None:
+        N.check(self._lib.b2v_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        N.check(self._lib.b2v_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def take_frames(self) -> list:
         with self._lock:
             out, self.frames = self.frames, []
