@@ -39,6 +39,13 @@ def lib():
     return _lib
 
 
+def set_threads(n: int = 0) -> int:
+    """Host threads for the oracle's OpenMP loops (0 = all cores); returns the count in effect."""
+    L = lib()
+    L.b2v_ref_set_threads(int(n))
+    return int(L.b2v_ref_max_threads())
+
+
 def _u8p(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 

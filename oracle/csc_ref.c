@@ -39,6 +39,25 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* host threads used by the OpenMP loops of the oracle (csc_ref.c, h264_ref.c); 0 = all */
+void b2v_ref_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+  (void)n;
+#endif
+}
+int b2v_ref_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 
 #define KYR 2991
 #define KYG 10064
@@ -108,6 +127,7 @@ int b2v_ref_csc_nv12(const uint8_t* bgra, int src_w, int src_h, int src_stride,
   if (!tx || !ty) { free(tx); free(ty); return -3; }
   make_taps(tx, dst_w, src_w);
   make_taps(ty, dst_h, src_h);
+#pragma omp parallel for schedule(static)
   for (int y = 0; y < coded_h; y += 2) {
     for (int x = 0; x < coded_w; x += 2) {
       int sb = 0, sg = 0, sr = 0;

@@ -159,7 +159,12 @@ class ArraySource(FrameSource):
     def fill(self, view, index):
         if index >= len(self.frames) and not self.loop:
             return False
-        view[...] = self.frames[index % len(self.frames)]
+        f = self.frames[index % len(self.frames)]
+        if f.shape != view.shape:        # the display was resized: nearest-neighbour resample of the canned frame
+            ys = (np.arange(view.shape[0]) * f.shape[0]) // view.shape[0]
+            xs = (np.arange(view.shape[1]) * f.shape[1]) // view.shape[1]
+            f = f[ys][:, xs]
+        view[...] = f
         return True
 
 
