@@ -311,19 +311,33 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
       for (int w = 0; w < SLICE_THREADS / 32; w++) m = max(m, s_warp_max[w]);
       s_carry_last = m;
     }
-    // each warp copies 32 macroblocks of the chunk, lanes stride over the macroblock's words
-    for (int k = 0; k < 32; k++) {
-      const int j = warp * 32 + k;
-      if (base + j >= n_mb) break;
-      const uint32_t nb = s_nb[j];
-      if (nb == 0xffffffffu) continue;
-      long long pos = s_off[j];
-      if (!f.idr) {
-        if (lane == 0) { GlobalSink g{out, pos}; put_ue(g, (uint32_t)s_run[j]); }
-        pos += ue_len((uint32_t)s_run[j]);
+    // phase 1 — one THREAD per macroblock: mb_skip_run prefix + the first HEAD_WORDS words (covers nearly
+    // every P macroblock completely, all 256 in parallel)
+    constexpr int HEAD_WORDS = 4;
+    if (i < n_mb && !skip) {
+      long long pos = s_off[tid];
+      if (!f.idr) { GlobalSink g{out, pos}; put_ue(g, (uint32_t)run); pos = g.pos; }
+      const uint32_t* src = f.mb_words + (size_t)(mb0 + i) * MB_WORDS;
+      const int nw = min(HEAD_WORDS, (int)((nbits + 31) >> 5));
+      uint32_t v[HEAD_WORDS];
+#pragma unroll
+      for (int w = 0; w < HEAD_WORDS; w++) v[w] = w < nw ? src[w] : 0u;
+#pragma unroll
+      for (int w = 0; w < HEAD_WORDS; w++) {
+        if (v[w]) {
+          const long long p = pos + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);
+          if (o == 0) atomicOr(&out[wi], v[w]);
+          else { atomicOr(&out[wi], v[w] >> o); atomicOr(&out[wi + 1], v[w] << (32 - o)); }
+        }
       }
+    }
+    // phase 2 — big macroblocks: warps take them round-robin, lanes stride over the remaining words
+    for (int j = warp; j < SLICE_THREADS && base + j < n_mb; j += SLICE_THREADS / 32) {
+      const uint32_t nb = s_nb[j];
+      if (nb == 0xffffffffu || nb <= 32u * HEAD_WORDS) continue;
+      const long long pos = s_off[j] + (f.idr ? 0 : ue_len((uint32_t)s_run[j]));
       const uint32_t* src = f.mb_words + (size_t)(mb0 + base + j) * MB_WORDS;
-      for (int w = lane; w < (int)((nb + 31) >> 5); w += 32) {
+      for (int w = HEAD_WORDS + lane; w < (int)((nb + 31) >> 5); w += 32) {
         const uint32_t v = src[w];
         if (v) {
           const long long p = pos + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);

@@ -25,6 +25,10 @@ struct InterSm {
   uint32_t win[WIN_ROWS][WIN_WORDS];
 };
 
+__device__ __forceinline__ uint32_t sad4acc(uint32_t a, uint32_t b, uint32_t c) {   // VABSDIFF4.U8.ACC with a live accumulator
+  uint32_t d; asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 __host__ __device__ constexpr int se_bits_c(int v) {
   unsigned c = (v > 0 ? 2u * (unsigned)v - 1u : (unsigned)(-2 * v)) + 1u;
   int len = 0;
@@ -54,11 +58,18 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
       *reinterpret_cast<uint2*>(&t.cur_uv[r8][c8]) = w;
     }
     const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
-    if (x_inside) {
-      for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
-        const int row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        const int y = clip3i(0, f.ch - 1, y0 - 16 + row);
-        sm.win[row][w] = __ldg(reinterpret_cast<const uint32_t*>(ref_y + (size_t)y * f.cw + x0 - 16) + w);
+    if (x_inside) {   // 576 words = 18 per lane: issue every load before the first shared-memory store
+      uint32_t v[18];
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref_y + x0 - 16);
+#pragma unroll
+      for (int k = 0; k < 18; k++) {
+        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        v[k] = __ldg(base + (size_t)clip3i(0, f.ch - 1, y0 - 16 + row) * (f.cw >> 2) + w);
+      }
+#pragma unroll
+      for (int k = 0; k < 18; k++) {
+        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        sm.win[row][w] = v[k];
       }
     } else {   // picture edge: per-sample clamping (8.4.2.2.1 reference sample padding)
       for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     for (int r = 0; r < 16; r++) {
       const int dyi = y - r;
       if (dyi >= 0 && dyi <= 32)
-        acc[dyi] = __vsadu4(c[r][0], a0) + (__vsadu4(c[r][1], a1) + (__vsadu4(c[r][2], a2) + (__vsadu4(c[r][3], a3) + acc[dyi])));
+        acc[dyi] = sad4acc(c[r][0], a0, sad4acc(c[r][1], a1, sad4acc(c[r][2], a2, sad4acc(c[r][3], a3, acc[dyi]))));
     }
   }
   const int lambda = me_lambda[qp];
