@@ -126,7 +126,28 @@ static void write_param_sets(enc_t* e) {
   int crop_r = (e->cw - e->width) / 2, crop_b = (e->ch - e->height) / 2;
   if (crop_r || crop_b) { bw_put(&b, 1, 1); bw_ue(&b, 0); bw_ue(&b, crop_r); bw_ue(&b, 0); bw_ue(&b, crop_b); }
   else bw_put(&b, 1, 0);
-  bw_put(&b, 1, 0);             /* vui_parameters_present_flag */
+  /* E.1.1 VUI: colour description (the CSC stage is BT.709 limited range, centre-sited chroma) and a
+   * bitstream restriction telling decoders there is no reordering (low-latency output) */
+  bw_put(&b, 1, 1);             /* vui_parameters_present_flag */
+  bw_put(&b, 1, 0);             /* aspect_ratio_info_present_flag */
+  bw_put(&b, 1, 0);             /* overscan_info_present_flag */
+  bw_put(&b, 1, 1);             /* video_signal_type_present_flag */
+  bw_put(&b, 3, 5);             /* video_format: unspecified */
+  bw_put(&b, 1, 0);             /* video_full_range_flag: limited */
+  bw_put(&b, 1, 1);             /* colour_description_present_flag */
+  bw_put(&b, 8, 1); bw_put(&b, 8, 1); bw_put(&b, 8, 1);   /* primaries / transfer / matrix = BT.709 */
+  bw_put(&b, 1, 1);             /* chroma_loc_info_present_flag */
+  bw_ue(&b, 1); bw_ue(&b, 1);   /* chroma_sample_loc_type top/bottom = 1 (centre) */
+  bw_put(&b, 1, 0);             /* timing_info_present_flag */
+  bw_put(&b, 1, 0);             /* nal_hrd_parameters_present_flag */
+  bw_put(&b, 1, 0);             /* vcl_hrd_parameters_present_flag */
+  bw_put(&b, 1, 0);             /* pic_struct_present_flag */
+  bw_put(&b, 1, 1);             /* bitstream_restriction_flag */
+  bw_put(&b, 1, 1);             /* motion_vectors_over_pic_boundaries_flag */
+  bw_ue(&b, 0); bw_ue(&b, 0);   /* max_bytes_per_pic_denom, max_bits_per_mb_denom */
+  bw_ue(&b, 10); bw_ue(&b, 10); /* log2_max_mv_length_horizontal / vertical */
+  bw_ue(&b, 0);                 /* max_num_reorder_frames */
+  bw_ue(&b, 1);                 /* max_dec_frame_buffering */
   bw_trailing(&b);
   e->sps_len = (int)nal_write(e->sps, 1, 3, 7, b.buf, b.pos);
   bw_free(&b);
@@ -225,6 +246,7 @@ static uint8_t* plane_uv(enc_t* e, int idx) { return e->recon[idx] + (size_t)e->
 
 static int slice_first_row(const enc_t* e, int mby) { return (mby / e->slice_rows) * e->slice_rows; }
 static int avail_top(const enc_t* e, int mby) { return mby > slice_first_row(e, mby); }
+static void make_pcm_if_too_big(enc_t* e, mb_t* m, const uint8_t* cur_nv12, int mbx, int mby);   /* defined after the CAVLC coder */
 
 /* ------------------------------------------------------------------ chroma: shared by I and P macroblocks */
 /* cur/pred: [2][64] raster 8x8 per component.  Writes levels, nnz_c, chroma cbp; reconstructs into the frame. */
@@ -391,6 +413,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   }
   int cbp_c = code_chroma(e, m, mbx, mby, qp, 1, cc, best_cpred);
   m->cbp = (uint8_t)((any_ac ? 15 : 0) | (cbp_c << 4));
+  make_pcm_if_too_big(e, m, cur_nv12, mbx, mby);
 }
 
 /* ------------------------------------------------------------------ inter macroblock (8.4) */
@@ -459,6 +482,7 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   }
   int cbp_c = code_chroma(e, m, mbx, mby, qp, 0, cc, pc);
   m->cbp = (uint8_t)(cbp | (cbp_c << 4));
+  make_pcm_if_too_big(e, m, cur_nv12, mbx, mby);
 }
 
 /* ------------------------------------------------------------------ CAVLC (9.2) */
@@ -469,7 +493,11 @@ static void cavlc_block(bitw_t* b, const int16_t* lv, int start, int maxc, int n
   int total = n, t1 = 0;
   for (int i = n - 1; i >= 0 && t1 < 3; i--) { if (iabs(lv[start + idx[i]]) == 1) t1++; else break; }
   if (nC == -1) bw_put(b, chroma_dc_coeff_token_len[4 * total + t1], chroma_dc_coeff_token_bits[4 * total + t1]);
-  else {
+  else if (nC == -2) {   /* size estimate before the neighbours are known: the longest coeff_token of the four tables */
+    int len = 0;
+    for (int t = 0; t < 4; t++) if (coeff_token_len[t][4 * total + t1] > len) len = coeff_token_len[t][4 * total + t1];
+    bw_put(b, len, 0);
+  } else {
     int tab = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3;
     bw_put(b, coeff_token_len[tab][4 * total + t1], coeff_token_bits[tab][4 * total + t1]);
   }
@@ -537,24 +565,27 @@ static int nnz_chroma_at(const enc_t* e, const uint8_t* skip, int mbx, int mby, 
 static int calc_nc(int na, int oka, int nb, int okb) { return oka && okb ? (na + nb + 1) >> 1 : oka ? na : okb ? nb : 0; }
 
 /* motion vector prediction for a 16x16 partition (8.4.1.3) and the P_Skip inference (8.4.1.1).
- * Every macroblock of a P picture here is inter with refIdx 0. */
-static void mv_neighbours(const enc_t* e, int mbx, int mby, int okv[3], int mv[3][2]) {
+ * Inter macroblocks have refIdx 0; intra (here: I_PCM) and unavailable neighbours count as refIdx -1, mv 0. */
+static void mv_neighbours(const enc_t* e, int mbx, int mby, int av[3], int ref0[3], int mv[3][2]) {
   int top = avail_top(e, mby);
   int nx[3] = { mbx - 1, mbx, mbx + 1 }, ny[3] = { mby, mby - 1, mby - 1 };
-  okv[0] = mbx > 0; okv[1] = top; okv[2] = top && mbx + 1 < e->mbw;
-  if (!okv[2]) { nx[2] = mbx - 1; okv[2] = top && mbx > 0; }    /* C unavailable -> D */
+  av[0] = mbx > 0; av[1] = top; av[2] = top && mbx + 1 < e->mbw;
+  if (!av[2]) { nx[2] = mbx - 1; av[2] = top && mbx > 0; }    /* C unavailable -> D */
   for (int i = 0; i < 3; i++) {
-    mv[i][0] = mv[i][1] = 0;
-    if (okv[i]) { const mb_t* n = &e->mbs[ny[i] * e->mbw + nx[i]]; mv[i][0] = n->mv[0]; mv[i][1] = n->mv[1]; }
+    mv[i][0] = mv[i][1] = 0; ref0[i] = 0;
+    if (av[i]) {
+      const mb_t* n = &e->mbs[ny[i] * e->mbw + nx[i]];
+      if (n->type == 1) { ref0[i] = 1; mv[i][0] = n->mv[0]; mv[i][1] = n->mv[1]; }
+    }
   }
 }
 static int median3(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : (c < mn ? mn : c); }
 static void mv_pred16(const enc_t* e, int mbx, int mby, int out[2]) {
-  int ok[3], mv[3][2];
-  mv_neighbours(e, mbx, mby, ok, mv);
-  if (!ok[1] && !ok[2] && ok[0]) { out[0] = mv[0][0]; out[1] = mv[0][1]; return; }
-  int cnt = ok[0] + ok[1] + ok[2];
-  if (cnt == 1) { int i = ok[0] ? 0 : ok[1] ? 1 : 2; out[0] = mv[i][0]; out[1] = mv[i][1]; return; }
+  int av[3], r0[3], mv[3][2];
+  mv_neighbours(e, mbx, mby, av, r0, mv);
+  if (!av[1] && !av[2] && av[0]) { out[0] = mv[0][0]; out[1] = mv[0][1]; return; }   /* B, C unavailable: all three become A */
+  int cnt = r0[0] + r0[1] + r0[2];
+  if (cnt == 1) { int i = r0[0] ? 0 : r0[1] ? 1 : 2; out[0] = mv[i][0]; out[1] = mv[i][1]; return; }
   out[0] = median3(mv[0][0], mv[1][0], mv[2][0]);
   out[1] = median3(mv[0][1], mv[1][1], mv[2][1]);
 }
@@ -563,8 +594,37 @@ static void mv_pred_skip(const enc_t* e, int mbx, int mby, int out[2]) {
   out[0] = out[1] = 0;
   if (!okA || !okB) return;
   const mb_t* a = &e->mbs[mby * e->mbw + mbx - 1]; const mb_t* b = &e->mbs[(mby - 1) * e->mbw + mbx];
-  if ((a->mv[0] == 0 && a->mv[1] == 0) || (b->mv[0] == 0 && b->mv[1] == 0)) return;
+  if ((a->type == 1 && a->mv[0] == 0 && a->mv[1] == 0) || (b->type == 1 && b->mv[0] == 0 && b->mv[1] == 0)) return;
   mv_pred16(e, mbx, mby, out);
+}
+
+/* Upper bound of the macroblock_layer() size: exact CAVLC cost of every coded block with the longest
+ * coeff_token of the four nC tables, plus 48 bits for mb_type / mvd / cbp / qp_delta.  A macroblock whose bound
+ * exceeds the 3200-bit limit of A.3.1 is sent as I_PCM instead (decided at analysis time because the
+ * reconstruction — which the following macroblocks predict from — becomes the source samples). */
+#define MB_BITS_LIMIT 3200
+static int mb_bits_estimate(const mb_t* m) {
+  bitw_t b; bw_init(&b);
+  if (m->type == 0) cavlc_block(&b, m->coef[0], 0, 16, -2);
+  for (int blk = 0; blk < 16; blk++) {
+    if (!(m->cbp & (1 << (blk >> 2)))) continue;
+    if (m->type == 0) cavlc_block(&b, m->coef[1 + blk], 1, 15, -2); else cavlc_block(&b, m->coef[1 + blk], 0, 16, -2);
+  }
+  int cc = m->cbp >> 4;
+  if (cc) { cavlc_block(&b, m->coef[17], 0, 4, -1); cavlc_block(&b, m->coef[18], 0, 4, -1); }
+  if (cc & 2) for (int k = 0; k < 8; k++) cavlc_block(&b, m->coef[19 + k], 1, 15, -2);
+  int bits = 48 + (int)bw_bits(&b);
+  bw_free(&b);
+  return bits;
+}
+static void make_pcm_if_too_big(enc_t* e, mb_t* m, const uint8_t* cur_nv12, int mbx, int mby) {
+  if (mb_bits_estimate(m) <= MB_BITS_LIMIT) return;
+  uint8_t* ry = plane_y(e, e->cur); uint8_t* ruv = plane_uv(e, e->cur);
+  const uint8_t* cuv = cur_nv12 + (size_t)e->cw * e->ch;
+  for (int r = 0; r < 16; r++) memcpy(ry + (size_t)(mby * 16 + r) * e->cw + mbx * 16, cur_nv12 + (size_t)(mby * 16 + r) * e->cw + mbx * 16, 16);
+  for (int r = 0; r < 8; r++) memcpy(ruv + (size_t)(mby * 8 + r) * e->cw + mbx * 16, cuv + (size_t)(mby * 8 + r) * e->cw + mbx * 16, 16);
+  m->type = 2; m->cbp = 0; m->mv[0] = m->mv[1] = 0;
+  memset(m->nnz_l, 16, sizeof m->nnz_l); memset(m->nnz_c, 16, sizeof m->nnz_c);
 }
 
 static void write_residual(const enc_t* e, bitw_t* b, const uint8_t* skip, const mb_t* m, int mbx, int mby) {
@@ -619,6 +679,15 @@ static size_t code_slice(enc_t* e, int s, int idr, int qp, uint8_t* skip, uint8_
         mv_pred_skip(e, mbx, mby, sp);
         if (m->type == 1 && m->cbp == 0 && m->mv[0] == sp[0] && m->mv[1] == sp[1]) { skip[mby * e->mbw + mbx] = 1; skip_run++; continue; }
         bw_ue(&b, skip_run); skip_run = 0;
+      }
+      if (m->type == 2) {                       /* I_PCM (7.3.5): mb_type 25 (+5 in P slices), alignment, raw samples */
+        bw_ue(&b, idr ? 25 : 30);
+        if (b.nacc) bw_put(&b, 8 - b.nacc, 0);  /* pcm_alignment_zero_bit */
+        const uint8_t* ry = plane_y(e, e->cur); const uint8_t* ruv = plane_uv(e, e->cur);
+        for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) bw_put(&b, 8, ry[(size_t)(mby * 16 + r) * e->cw + mbx * 16 + c]);
+        for (int k = 0; k < 2; k++)
+          for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) bw_put(&b, 8, ruv[(size_t)(mby * 8 + r) * e->cw + (mbx * 8 + c) * 2 + k]);
+        continue;
       }
       if (m->type == 0) {
         int t = 1 + m->i16_mode + 4 * (m->cbp >> 4) + ((m->cbp & 15) ? 12 : 0);

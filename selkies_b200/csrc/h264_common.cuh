@@ -7,11 +7,13 @@
 #include <stdint.h>
 
 #include "h264_tables.cuh"
+#include "h264_cavlc.cuh"
 
 namespace b2v {
 
 constexpr int MB_I16 = 0, MB_P16 = 1, MB_PCM = 2;
 constexpr int COEF_BLOCKS = 27;            // 0 luma DC | 1..16 luma | 17,18 chroma DC | 19..26 chroma AC
+constexpr int MB_BITS_LIMIT = 3200;         // A.3.1: bits of macroblock_layer() per macroblock
 constexpr int MB_WORDS = 128;              // per-macroblock bit scratch: 128 x u32 = 4096 bits
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -170,6 +172,7 @@ struct MbTile {
   uint8_t rec_uv[8][16];
   int dc[16];                // luma DC exchange (raster block position)
   int dcl[16];
+  int16_t lvs[COEF_BLOCKS][16];   // scan-order levels of every block, for the I_PCM size check
 };
 
 // Lanes 0..15: luma block `lane` (blkIdx), lanes 16..23: chroma.  Reads cur/pred from the tile, writes levels,
@@ -232,6 +235,7 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
     if (is_luma) {
       // scan-order store of the DC levels: lane k writes level at raster zigzag4x4[k]
       coef_mb[lane] = (int16_t)t.dcl[zigzag4x4[lane]];
+      t.lvs[0][lane] = (int16_t)t.dcl[zigzag4x4[lane]];
       const int r = (by >> 2) * 4 + (bx >> 2), i = r >> 2, j = r & 3;
       int acc = 0;
 #pragma unroll
@@ -269,6 +273,7 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
       dc_deq = ((fq * (16 * q.dq[0])) << q.qshift) >> 5;
       // chroma DC levels: coef block 17 + comp, entries 0..3 (rest zero)
       coef_mb[(17 + comp) * 16 + b] = (int16_t)cdc_level;
+      t.lvs[17 + comp][b] = (int16_t)cdc_level;
     }
   }
   // ---- reconstruction into the tile -------------------------------------------------------------
@@ -284,6 +289,7 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
       *reinterpret_cast<uint32_t*>(&t.rec_y[by + i][bx]) = o;
     }
     store_levels(coef_mb + (1 + lane) * 16, lv);
+    store_levels(&t.lvs[1 + lane][0], lv);
     nnz_mb[(by >> 2) * 4 + (bx >> 2)] = (uint8_t)n;
   } else if (is_chroma) {
     recon_block<true>(lv, q, dc_deq, resid);
@@ -292,6 +298,7 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
 #pragma unroll
       for (int j = 0; j < 4; j++) t.rec_uv[by + i][(bx + j) * 2 + comp] = (uint8_t)clip255((int)t.pred_uv[by + i][(bx + j) * 2 + comp] + resid[4 * i + j]);
     store_levels(coef_mb + (19 + (lane - 16)) * 16, lv);
+    store_levels(&t.lvs[19 + (lane - 16)][0], lv);
     nnz_mb[16 + (lane - 16)] = (uint8_t)n;
   }
   // ---- coded block pattern -----------------------------------------------------------------------
@@ -301,6 +308,27 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
   if (INTRA16) cbp_l = (nzmask & 0xffffu) ? 15 : 0;
   else cbp_l = ((nzmask & 0x000fu) ? 1 : 0) | ((nzmask & 0x00f0u) ? 2 : 0) | ((nzmask & 0x0f00u) ? 4 : 0) | ((nzmask & 0xf000u) ? 8 : 0);
   int cbp_c = (nzmask & 0xff0000u) ? 2 : (dcmask ? 1 : 0);
+  // ---- I_PCM decision: upper bound of macroblock_layer() bits = exact CAVLC size of every coded
+  // block with the longest coeff_token of the four nC tables + 48 header bits; above the 3200-bit limit of A.3.1
+  // the macroblock is sent raw and its reconstruction becomes the source samples. -------------------------------
+  __syncwarp();
+  {
+    bool coded = false; int start = 0, maxc = 16, nC = NC_WORST;
+    if (lane == 0) coded = INTRA16;
+    else if (lane <= 16) { coded = (cbp_l >> ((lane - 1) >> 2)) & 1; if (INTRA16) { start = 1; maxc = 15; } }
+    else if (lane <= 18) { coded = cbp_c != 0; maxc = 4; nC = NC_CHROMA_DC; }
+    else if (lane <= 26) { coded = cbp_c == 2; start = 1; maxc = 15; }
+    CountSink cs;
+    if (coded) cavlc_block(cs, &t.lvs[lane][start], maxc, nC);
+    const int est = 48 + __reduce_add_sync(FULL, cs.n);
+    if (est > MB_BITS_LIMIT) {
+      const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+      *reinterpret_cast<uint2*>(&t.rec_y[r8][c8]) = *reinterpret_cast<const uint2*>(&t.cur_y[r8][c8]);
+      if (lane < 16) *reinterpret_cast<uint2*>(&t.rec_uv[r8][c8]) = *reinterpret_cast<const uint2*>(&t.cur_uv[r8][c8]);
+      if (lane < 24) nnz_mb[lane] = 16;
+      return -1;
+    }
+  }
   return cbp_l | (cbp_c << 4);
 }
 

@@ -81,7 +81,19 @@ std::vector<uint8_t> make_param_sets(const EncoderConfig& c, int mbw, int mbh) {
   b.put(1, 1);             // direct_8x8_inference_flag
   const int crop_r = (c.coded_w - c.width) / 2, crop_b = (c.coded_h - c.height) / 2;
   if (crop_r || crop_b) { b.put(1, 1); b.ue(0); b.ue(crop_r); b.ue(0); b.ue(crop_b); } else b.put(1, 0);
-  b.put(1, 0);             // vui_parameters_present_flag
+  // E.1.1 VUI: BT.709 limited-range colour description, centre-sited chroma, no picture reordering
+  b.put(1, 1);             // vui_parameters_present_flag
+  b.put(1, 0); b.put(1, 0);        // aspect_ratio_info_present_flag, overscan_info_present_flag
+  b.put(1, 1); b.put(3, 5); b.put(1, 0); b.put(1, 1);   // video_signal_type: format 5, limited range, colour description
+  b.put(8, 1); b.put(8, 1); b.put(8, 1);               // primaries / transfer / matrix = BT.709
+  b.put(1, 1); b.ue(1); b.ue(1);   // chroma_loc_info: type 1 (centre) for both fields
+  b.put(1, 0); b.put(1, 0); b.put(1, 0); b.put(1, 0);   // timing_info, nal_hrd, vcl_hrd, pic_struct
+  b.put(1, 1);             // bitstream_restriction_flag
+  b.put(1, 1);             // motion_vectors_over_pic_boundaries_flag
+  b.ue(0); b.ue(0);        // max_bytes_per_pic_denom, max_bits_per_mb_denom
+  b.ue(10); b.ue(10);      // log2_max_mv_length_horizontal / vertical
+  b.ue(0);                 // max_num_reorder_frames
+  b.ue(1);                 // max_dec_frame_buffering
   b.trailing();
   append_nal(out, 3, 7, b.buf);
   HostBits p;

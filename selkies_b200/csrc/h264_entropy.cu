@@ -14,106 +14,41 @@
 //                 start codes + NAL headers, AuHeader, and the frame-level rate-controller update.
 // CPU restatement: oracle/h264_ref.c cavlc_block(), code_slice(), nal_write(), rc_update().
 #include "h264_common.cuh"
+#include "h264_cavlc.cuh"
 #include "h264_encoder.h"
 #include "h264_kernels.h"
 
 namespace b2v {
 
-// ------------------------------------------------------------------------------------------------ bit sinks
-struct CountSink {
-  int n = 0;
-  __device__ __forceinline__ void put(int len, uint32_t) { n += len; }
-};
-struct SmemSink {           // MSB-first into big-endian u32 words, concurrent writers use atomicOr
-  uint32_t* w; int pos; int cap_bits;
-  __device__ __forceinline__ void put(int len, uint32_t v) {
-    if (len == 0) return;
-    if (pos + len <= cap_bits) {
-      const int wi = pos >> 5, o = pos & 31, space = 32 - o;
-      if (len <= space) atomicOr(&w[wi], v << (space - len));
-      else { atomicOr(&w[wi], v >> (len - space)); atomicOr(&w[wi + 1], v << (32 - (len - space))); }
-    }
-    pos += len;
-  }
-};
-template <class S> __device__ __forceinline__ void put_ue(S& s, uint32_t v) { const int len = 31 - __clz(v + 1); s.put(2 * len + 1, v + 1); }
-template <class S> __device__ __forceinline__ void put_se(S& s, int v) { put_ue(s, v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
-__device__ __forceinline__ int ue_len(uint32_t v) { return 2 * (31 - __clz(v + 1)) + 1; }
-
-// ------------------------------------------------------------------------------------------------ residual block (9.2)
-template <class S>
-__device__ __forceinline__ void cavlc_block(S& s, const int16_t* lv /* scan order, already offset by start */, int maxc, int nC) {
-  uint32_t nz = 0, ones = 0;
-  for (int k = 0; k < maxc; k++) { const int v = lv[k]; nz |= (uint32_t)(v != 0) << k; ones |= (uint32_t)(v == 1 || v == -1) << k; }
-  const int total = __popc(nz);
-  int t1 = 0;
-  { uint32_t m = nz; while (m && t1 < 3) { const int top = 31 - __clz(m); if (!((ones >> top) & 1)) break; t1++; m ^= 1u << top; } }
-  if (nC < 0) s.put(chroma_dc_coeff_token_len[4 * total + t1], chroma_dc_coeff_token_bits[4 * total + t1]);
-  else { const int tab = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3; s.put(coeff_token_len[tab][4 * total + t1], coeff_token_bits[tab][4 * total + t1]); }
-  if (!total) return;
-  uint32_t m = nz;
-  for (int i = 0; i < t1; i++) { const int top = 31 - __clz(m); s.put(1, lv[top] < 0 ? 1u : 0u); m ^= 1u << top; }
-  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
-  bool first = true;
-  while (m) {
-    const int top = 31 - __clz(m); m ^= 1u << top;
-    const int level = lv[top];
-    int code = level > 0 ? 2 * level - 2 : -2 * level - 1;
-    if (first && t1 < 3) code -= 2;
-    first = false;
-    if (suffix_len == 0) {
-      if (code < 14) s.put(code + 1, 1);
-      else if (code < 30) { s.put(15, 1); s.put(4, (uint32_t)(code - 14)); }
-      else { s.put(16, 1); s.put(12, (uint32_t)(code - 30)); }
-    } else {
-      if (code < (15 << suffix_len)) { s.put((code >> suffix_len) + 1, 1); s.put(suffix_len, (uint32_t)(code & ((1 << suffix_len) - 1))); }
-      else { s.put(16, 1); s.put(12, (uint32_t)(code - (15 << suffix_len))); }
-    }
-    if (suffix_len == 0) suffix_len = 1;
-    if (abs(level) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
-  }
-  const int zeros = (31 - __clz(nz)) + 1 - total;
-  if (total < maxc) {
-    if (nC < 0) s.put(chroma_dc_total_zeros_len[total - 1][zeros], chroma_dc_total_zeros_bits[total - 1][zeros]);
-    else s.put(total_zeros_len[total - 1][zeros], total_zeros_bits[total - 1][zeros]);
-  }
-  int left = zeros;
-  m = nz;
-  while (left > 0 && (m & (m - 1))) {
-    const int top = 31 - __clz(m); m ^= 1u << top;
-    const int run = top - (31 - __clz(m)) - 1;
-    const int tix = min(left, 7) - 1;
-    s.put(run_len[tix][run], run_bits[tix][run]);
-    left -= run;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ mv prediction (8.4.1.3, 8.4.1.1)
 __device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
 
-struct MvCtx { bool okA, okB, okC; int ax, ay, bx, by, cx, cy; };
+// avX: neighbour partition available (inside the slice); rX: it is an inter macroblock with refIdx 0.
+// Intra (I_PCM) and unavailable neighbours contribute mv 0 / refIdx -1.
+struct MvCtx { bool avA, avB, avC, rA, rB, rC; int ax, ay, bx, by, cx, cy; };
 __device__ __forceinline__ MvCtx mv_ctx(const FrameCtx& f, int mbx, int mby) {
   MvCtx m;
   const bool top = top_in_slice(f, mby);
-  m.okA = mbx > 0; m.okB = top; m.okC = top && mbx + 1 < f.mbw;
+  m.avA = mbx > 0; m.avB = top; m.avC = top && mbx + 1 < f.mbw;
   int cxi = mbx + 1;
-  if (!m.okC) { cxi = mbx - 1; m.okC = top && mbx > 0; }      // C unavailable -> D
+  if (!m.avC) { cxi = mbx - 1; m.avC = top && mbx > 0; }      // C unavailable -> D
   m.ax = m.ay = m.bx = m.by = m.cx = m.cy = 0;
-  if (m.okA) { const MbInfo a = f.mbinfo[mby * f.mbw + mbx - 1]; m.ax = a.mvx; m.ay = a.mvy; }
-  if (m.okB) { const MbInfo b = f.mbinfo[(mby - 1) * f.mbw + mbx]; m.bx = b.mvx; m.by = b.mvy; }
-  if (m.okC) { const MbInfo c = f.mbinfo[(mby - 1) * f.mbw + cxi]; m.cx = c.mvx; m.cy = c.mvy; }
+  m.rA = m.rB = m.rC = false;
+  if (m.avA) { const MbInfo a = f.mbinfo[mby * f.mbw + mbx - 1]; if (a.type == MB_P16) { m.rA = true; m.ax = a.mvx; m.ay = a.mvy; } }
+  if (m.avB) { const MbInfo b = f.mbinfo[(mby - 1) * f.mbw + mbx]; if (b.type == MB_P16) { m.rB = true; m.bx = b.mvx; m.by = b.mvy; } }
+  if (m.avC) { const MbInfo c = f.mbinfo[(mby - 1) * f.mbw + cxi]; if (c.type == MB_P16) { m.rC = true; m.cx = c.mvx; m.cy = c.mvy; } }
   return m;
 }
 __device__ __forceinline__ void mv_pred16(const MvCtx& m, int& px, int& py) {
-  if (!m.okB && !m.okC && m.okA) { px = m.ax; py = m.ay; return; }
-  const int cnt = (int)m.okA + (int)m.okB + (int)m.okC;
-  if (cnt == 1) { px = m.okA ? m.ax : m.okB ? m.bx : m.cx; py = m.okA ? m.ay : m.okB ? m.by : m.cy; return; }
+  if (!m.avB && !m.avC && m.avA) { px = m.ax; py = m.ay; return; }
+  const int cnt = (int)m.rA + (int)m.rB + (int)m.rC;
+  if (cnt == 1) { px = m.rA ? m.ax : m.rB ? m.bx : m.cx; py = m.rA ? m.ay : m.rB ? m.by : m.cy; return; }
   px = median3(m.ax, m.bx, m.cx); py = median3(m.ay, m.by, m.cy);
 }
 __device__ __forceinline__ void mv_pred_skip(const MvCtx& m, int& px, int& py) {
   px = py = 0;
-  if (!m.okA || !m.okB) return;
-  if ((m.ax == 0 && m.ay == 0) || (m.bx == 0 && m.by == 0)) return;
+  if (!m.avA || !m.avB) return;
+  if ((m.rA && m.ax == 0 && m.ay == 0) || (m.rB && m.bx == 0 && m.by == 0)) return;
   mv_pred16(m, px, py);
 }
 
@@ -146,6 +81,15 @@ __global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
   }
   if (skip) {                                    // P_Skip: no bits; k_slice_bits folds it into mb_skip_run
     if (lane == 0) f.mb_nbits[mb] = 0x80000000u;
+    return;
+  }
+  if (mi.type == MB_PCM) {                       // I_PCM: only mb_type here; alignment + 384 raw samples are placed by k_slice_bits
+    if (lane == 0) {
+      const uint32_t code = f.idr ? 25u : 30u;
+      const int len = 2 * (31 - __clz(code + 1)) + 1;
+      f.mb_words[(size_t)mb * MB_WORDS] = (code + 1) << (32 - len);
+      f.mb_nbits[mb] = (uint32_t)len | 0x40000000u;
+    }
     return;
   }
   // ---- which block does this lane code, and with which nC ---------------------------------------------
@@ -275,8 +219,11 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
   __syncthreads();
   for (int base = 0; base < n_mb; base += SLICE_THREADS) {
     const int i = base + tid;
-    uint32_t nbits = 0; bool skip = true;
-    if (i < n_mb) { const uint32_t v = f.mb_nbits[mb0 + i]; skip = (v >> 31) != 0; nbits = v & 0x7fffffffu; }
+    uint32_t nbits = 0; bool skip = true, pcm = false;
+    if (i < n_mb) { const uint32_t v = f.mb_nbits[mb0 + i]; skip = (v >> 31) != 0; pcm = ((v >> 30) & 1u) != 0; nbits = v & 0x3fffffffu; }
+    // I_PCM samples must start byte-aligned in the RBSP, so a macroblock's length then depends on its position:
+    // chunks containing one (pathological content only) get their offsets from a serial walk below.
+    const bool any_pcm = __syncthreads_or(pcm) != 0;
     // last non-skipped index strictly before i  (max-scan)
     int mine = skip ? -1 : i;
     int incl_max = mine;
@@ -297,19 +244,34 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
     if (lane == 31) s_warp_sum[warp] = incl;
     __syncthreads();
-    long long woff = s_carry_bits;
+    const long long chunk_base = s_carry_bits;
+    long long woff = chunk_base;
     for (int w = 0; w < warp; w++) woff += s_warp_sum[w];
     s_off[tid] = woff + incl - tot;
-    s_nb[tid] = skip ? 0xffffffffu : nbits;
+    s_nb[tid] = skip ? 0xffffffffu : (nbits | (pcm ? 0x40000000u : 0u));
     s_run[tid] = run;
     __syncthreads();
     if (tid == SLICE_THREADS - 1) {
-      long long t = s_carry_bits;
+      long long t = chunk_base;
       for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_warp_sum[w];
-      s_carry_bits = t;
+      if (!any_pcm) s_carry_bits = t;
       int m = s_carry_last;
       for (int w = 0; w < SLICE_THREADS / 32; w++) m = max(m, s_warp_max[w]);
       s_carry_last = m;
+    }
+    if (any_pcm) {
+      if (tid == 0) {
+        long long pos = chunk_base;
+        for (int j = 0; j < SLICE_THREADS && base + j < n_mb; j++) {
+          const uint32_t nb = s_nb[j];
+          if (nb == 0xffffffffu) continue;
+          s_off[j] = pos;
+          pos += (f.idr ? 0 : ue_len((uint32_t)s_run[j])) + (nb & 0x3fffffffu);
+          if (nb & 0x40000000u) pos = ((pos + 7) & ~7LL) + 384 * 8;
+        }
+        s_carry_bits = pos;
+      }
+      __syncthreads();
     }
     // phase 1 — one THREAD per macroblock: mb_skip_run prefix + the first HEAD_WORDS words (covers nearly
     // every P macroblock completely, all 256 in parallel)
@@ -334,7 +296,26 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     // phase 2 — big macroblocks: warps take them round-robin, lanes stride over the remaining words
     for (int j = warp; j < SLICE_THREADS && base + j < n_mb; j += SLICE_THREADS / 32) {
       const uint32_t nb = s_nb[j];
-      if (nb == 0xffffffffu || nb <= 32u * HEAD_WORDS) continue;
+      if (nb == 0xffffffffu) continue;
+      if (nb & 0x40000000u) {     // I_PCM payload: 256 luma, 64 Cb, 64 Cr samples from the reconstruction (== source)
+        const long long pp = ((s_off[j] + (f.idr ? 0 : ue_len((uint32_t)s_run[j])) + (nb & 0x3fffffffu) + 7) & ~7LL);
+        const int mbi = mb0 + base + j, px = (mbi % f.mbw) * 16, py = (mbi / f.mbw) * 16;
+        const uint8_t* ry = f.recon; const uint8_t* ruv = f.recon + (size_t)f.cw * f.ch;
+        for (int w = lane; w < 96; w += 32) {
+          uint32_t v;
+          if (w < 64) v = __byte_perm(__ldcg(reinterpret_cast<const uint32_t*>(ry + (size_t)(py + (w >> 2)) * f.cw + px + (w & 3) * 4)), 0, 0x0123);
+          else {
+            const int k = (w - 64) & 15, comp = (w - 64) >> 4;
+            const uint2 q = __ldcg(reinterpret_cast<const uint2*>(ruv + (size_t)(py / 2 + (k >> 1)) * f.cw + px + (k & 1) * 8));
+            v = comp == 0 ? __byte_perm(q.x, q.y, 0x0246) : __byte_perm(q.x, q.y, 0x1357);
+          }
+          const long long p = pp + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);
+          if (o == 0) atomicOr(&out[wi], v);
+          else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
+        }
+        continue;
+      }
+      if (nb <= 32u * HEAD_WORDS) continue;
       const long long pos = s_off[j] + (f.idr ? 0 : ue_len((uint32_t)s_run[j]));
       const uint32_t* src = f.mb_words + (size_t)(mb0 + base + j) * MB_WORDS;
       for (int w = HEAD_WORDS + lane; w < (int)((nb + 31) >> 5); w += 32) {

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     }
     if (lane == 0) {
       MbInfo mi; mi.mvx = (int16_t)(4 * dx); mi.mvy = (int16_t)(4 * dy); mi.type = MB_P16; mi.i16_mode = 0; mi.chroma_mode = 0; mi.cbp = (uint8_t)cbp;
+      if (cbp < 0) { mi.mvx = 0; mi.mvy = 0; mi.type = MB_PCM; mi.cbp = 0; }   // too big for CAVLC: I_PCM (transform_mb)
       f.mbinfo[mb] = mi;
     }
   }

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       else nb.left_uv[lane - 16] = t.rec_uv[(lane - 16) >> 1][14 + ((lane - 16) & 1)];
       if (lane == 0) {
         MbInfo mi; mi.mvx = 0; mi.mvy = 0; mi.type = MB_I16; mi.i16_mode = (uint8_t)best_mode; mi.chroma_mode = (uint8_t)cbest; mi.cbp = (uint8_t)cbp;
+        if (cbp < 0) { mi.type = MB_PCM; mi.cbp = 0; }   // too big for CAVLC: I_PCM (transform_mb)
         f.mbinfo[mb] = mi;
       }
     }

@@ -67,6 +67,23 @@ def test_motion_and_noise_bit_exact():
     assert_same(*encode_both(192, 112, frames, qp=22, slice_rows=2))
 
 
+@pytest.mark.parametrize("qp,slice_rows", [(0, 1), (6, 2), (14, 1)])
+def test_pcm_fallback_bit_exact(qp, slice_rows):
+    """Macroblocks whose CAVLC size bound exceeds 3200 bits are sent as I_PCM (I and P slices)."""
+    w, h = 128, 96
+    frames = []
+    for t in range(3):
+        f = synth.desktop(w, h, t)
+        f[:48] = synth.noise(w, 48, t + 5)          # top half: incompressible at low QP -> I_PCM; bottom: ordinary
+        frames.append(f)
+    got, ref, grec, rrec = encode_both(w, h, frames, qp=qp, slice_rows=slice_rows)
+    assert_same(got, ref, grec, rrec)
+    if qp <= 6:
+        assert len(got[1].data) > 24 * 384           # the P picture still carries the raw macroblocks
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert len(dec) == 3 and np.array_equal(dec[2][0], grec[0][:h, :w])
+
+
 def test_static_scene_is_skipped():
     f = synth.desktop(320, 192, 0)
     got, ref, grec, rrec = encode_both(320, 192, [f, f, f], qp=30)
