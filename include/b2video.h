@@ -58,7 +58,7 @@ typedef struct b2v_settings {
   int32_t device;           /* CUDA ordinal (settings.py:162 gpu_id)                        */
   int32_t rc_mode;          /* B2V_RC_CBR | B2V_RC_CQP                                      */
   int32_t bitrate_kbps;     /* CaptureSettings.h264_bitrate_kbps                            */
-  int32_t crf;              /* CaptureSettings.h264_crf → constant QP in CQP mode           */
+  int32_t crf;              /* CaptureSettings.h264_crf → constant QP 0..51 in CQP mode; <0 = 26 */
   int32_t gop;              /* <=0: IDR only on request (settings.py:163 keyframe_distance=-1);
                                1: intra-only; N: IDR every N frames                         */
   int32_t slice_rows;       /* macroblock rows per slice (>=1); 0 = library default (1)      */

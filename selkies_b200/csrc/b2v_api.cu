@@ -334,7 +334,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   if (s->n_slots > kMaxSlots) s->n_slots = kMaxSlots;
   s->fps = cfg->fps > 0 ? cfg->fps : 60.0;
   s->bitrate_kbps = cfg->bitrate_kbps > 0 ? cfg->bitrate_kbps : 8000;
-  s->qp_fixed = cfg->crf > 0 ? cfg->crf : 26;
+  s->qp_fixed = cfg->crf >= 0 ? cfg->crf : 26;     // 0 is a valid QP; negative = library default
   if (s->qp_fixed > 51) s->qp_fixed = 51;
   s->cb = cb; s->user = user;
   cudaDeviceProp prop;
