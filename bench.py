@@ -18,6 +18,7 @@ run here — SURVEY.md §8c — so the arm runs the oracle port, all host thread
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -146,6 +147,31 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def rtp_leg(aus):
+    """native RTP H.264 payloader vs the Python restatement of the reference's (host code)."""
+    if not aus:
+        return None
+    try:
+        from oracle import rtp_ref
+        from selkies_b200.rtp_h264 import H264Payloader
+        pl = H264Payloader()
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for au in aus:
+                n = len(pl.packetize(au))
+        t_native = (time.perf_counter() - t0) / (reps * len(aus))
+        t0 = time.perf_counter()
+        for au in aus:
+            ref = rtp_ref.pack_access_unit(au)
+        t_py = (time.perf_counter() - t0) / len(aus)
+        same = all(pl.packetize(au) == rtp_ref.pack_access_unit(au) for au in aus)
+        return {"au_bytes": sum(map(len, aus)) / len(aus), "packets_per_au": len(ref), "native_us_per_au": t_native * 1e6,
+                "python_reference_port_us_per_au": t_py * 1e6, "identical_payloads": same}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def workload_config(frames_per_step):
     return {"workload": "C2: 3840x2160 synthetic desktop BGRA -> fused BT.709 CSC -> H.264 CBP (IDR then P, full-pel exhaustive ME +-16, CAVLC)",
             "frames_per_step": frames_per_step, "rate_control": f"CBR {BITRATE_KBPS} kbit/s @ {FPS_NOMINAL:g} fps nominal, free-running",
@@ -205,9 +231,12 @@ def main():
     sess = Session(W, H, fps=FPS_NOMINAL, device=local_rank, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS,
                    ring_slots=N_DISTINCT, flags=flags, collect=False)
     out_bytes = [0]
+    sample_aus = []
 
     def on_frame(fptr):
         out_bytes[0] += fptr.contents.size
+        if len(sample_aus) < 8 and not fptr.contents.is_key:
+            sample_aus.append(ctypes.string_at(fptr.contents.data, fptr.contents.size))
     sess._on_frame = on_frame
 
     # ---------------- leg 1: inputs resident in HBM ----------------------------------------------------
@@ -329,7 +358,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "wall_ms": e2e_wall_ms, "device_ms": e2e_dev_ms, "access_unit_bytes_per_frame": out_bytes[0] / max(1, n_frames)},
             "gpu_launches": int(st["kernel_launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "kernels_us": kern, "wall_ms_resident": wall_ms, "target_fps": 240,
+            "kernels_us": kern, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

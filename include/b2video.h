@@ -144,6 +144,14 @@ int  b2v_timer_start(void* h);
 int  b2v_timer_stop(void* h, float* ms);
 const char* b2v_last_error(void);
 
+/* ---- RTP H.264 payloader: replaces H264Encoder.pack -> _split_bitstream / _packetize
+ *      (src/selkies/webrtc/codecs/h264.py:238-279, 331-335).  Splits the Annex-B access unit and writes the RTP
+ *      payloads (single NAL, STAP-A, FU-A; RFC 6184 packetization-mode 1) back to back into `out`; lens[i] is the
+ *      size of payload i.  Byte-identical to the reference (tests/golden/rtp_h264_golden.json).  Host code, no GPU.
+ *      Returns B2V_ENOMEM when out/lens are too small (out_cap >= au_size + au_size/600 + 64 always suffices). */
+int  b2v_rtp_h264_packetize(const uint8_t* au, int32_t au_size, int32_t packet_max, uint8_t* out, int32_t out_cap,
+                            int32_t* lens, int32_t max_packets, int32_t* n_packets);
+
 #ifdef __cplusplus
 }
 #endif
