@@ -180,3 +180,26 @@ def test_session_sharding_rule():
     assert [session_device(i, 8) for i in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
     with pytest.raises(ValueError):
         session_device(0, 0)
+
+
+def test_c_abi_argument_errors_without_a_gpu():
+    """Error behaviour of the boundary: bad arguments give B2V_EINVAL + a message, never a crash (no CUDA call is reached)."""
+    import ctypes as C
+    from selkies_b200 import _native as N
+    lib = N.lib()
+    h = C.c_void_p()
+    s = N.B2VSettings()
+    s.src_w, s.src_h, s.fps = 1921, 1080, 60.0                       # odd width
+    assert lib.b2v_create(C.byref(s), N.FRAME_CB(lambda f, u: None), None, C.byref(h)) == N.B2V_EINVAL
+    assert b"unsupported" in lib.b2v_last_error()
+    s.src_w, s.src_h = 8192, 4320                                    # beyond 7680x4320 (selkies.py:281)
+    assert lib.b2v_create(C.byref(s), N.FRAME_CB(lambda f, u: None), None, C.byref(h)) == N.B2V_EINVAL
+    assert lib.b2v_create(None, N.FRAME_CB(lambda f, u: None), None, C.byref(h)) == N.B2V_EINVAL
+    for fn, args in ((lib.b2v_flush, (None,)), (lib.b2v_request_idr, (None,)), (lib.b2v_set_framerate, (None, 30.0)),
+                     (lib.b2v_set_bitrate_kbps, (None, 1000)), (lib.b2v_get_stats, (None, None))):
+        assert fn(*args) == N.B2V_EINVAL
+    lib.b2v_destroy(None)                                            # no-op
+    n = C.c_int32()
+    assert lib.b2v_rtp_h264_packetize(None, 0, 1300, None, 0, None, 0, C.byref(n)) == N.B2V_EINVAL
+    with pytest.raises(N.B2VError):
+        N.check(N.B2V_EINVAL)

@@ -1,0 +1,64 @@
+"""PSNR / bitrate table of the CUDA encoder (SURVEY.md §8c.4 iii: decoded-vs-source PSNR per config and bitrate).
+Run on the GPU box:  python tools/psnr_report.py  -> gpurun_out/psnr_report.json
+The x264 comparator is absent from this image (probed at run time), so the table is absolute."""
+import json, os, shutil, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import oracle
+from oracle import avdec
+from selkies_b200 import _native as N
+from selkies_b200.session import Session
+from tests import synth
+
+
+def content(name, w, h, n):
+    if name == "desktop_scroll":
+        return [synth.desktop(w, h, t) for t in range(n)]
+    if name == "bars_box":
+        return [synth.bars(w, h, t) for t in range(n)]
+    if name == "gradient_pan":
+        return [synth.gradient(w, h, t) for t in range(n)]
+    if name == "static_desktop":
+        f = synth.desktop(w, h, 0)
+        return [f] * n
+    raise ValueError(name)
+
+
+def run(w, h, name, kbps, fps, n):
+    frames = content(name, w, h, n)
+    with Session(w, h, fps=fps, rc_mode=N.B2V_RC_CBR, bitrate_kbps=kbps, ring_slots=4) as s:
+        for f in frames:
+            s.submit(f)
+        s.flush()
+        got = s.take_frames()
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert len(dec) == n
+    ps = []
+    for (Y, U, V), f in zip(dec, frames):
+        sy, suv = oracle.csc_nv12(f)
+        ps.append((avdec.psnr(Y, sy), avdec.psnr(U, suv[:, 0::2]), avdec.psnr(V, suv[:, 1::2])))
+    sizes = [len(g.data) for g in got]
+    tail = slice(n // 3, None)      # steady state: after the IDR burst has been absorbed
+    return {"w": w, "h": h, "content": name, "target_kbps": kbps, "fps": fps, "frames": n,
+            "achieved_kbps_steady": float(np.mean(sizes[tail]) * 8 * fps / 1000), "idr_bytes": sizes[0],
+            "psnr_y_steady": float(np.mean([p[0] for p in ps[tail]])), "psnr_u_steady": float(np.mean([p[1] for p in ps[tail]])),
+            "psnr_v_steady": float(np.mean([p[2] for p in ps[tail]])), "psnr_y_idr": ps[0][0],
+            "qp_first_last": [got[0].qp, got[-1].qp]}
+
+
+def main():
+    os.makedirs("gpurun_out", exist_ok=True)
+    rows = []
+    for (w, h) in [(1920, 1080), (3840, 2160)]:
+        for name in ["desktop_scroll", "bars_box", "gradient_pan", "static_desktop"]:
+            for kbps in [8000, 20000, 50000, 100000]:
+                r = run(w, h, name, kbps, 60.0, 30 if w == 1920 else 18)
+                rows.append(r)
+                print(json.dumps(r), flush=True)
+    out = {"x264_comparator": shutil.which("x264") or "absent", "gst_launch": shutil.which("gst-launch-1.0") or "absent",
+           "rate_control": "CBR (settings.py:49 range 1-100 Mbps)", "rows": rows}
+    json.dump(out, open("gpurun_out/psnr_report.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
