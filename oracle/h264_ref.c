@@ -721,7 +721,7 @@ static void rc_update(enc_t* e, int64_t bits, int64_t target, int idr) {
   if (target < 1) target = 1;
   int64_t ref = idr ? 4 * target : target;
   int64_t r = bits * 16 / ref;
-  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
+  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 1 ? -4 : r <= 4 ? -2 : r <= 13 ? -1 : 0;   /* r <= 1: (nearly) all-skip picture -> refine quickly */
   e->rc_fullness += bits - target;
   if (e->rc_fullness < -4 * target) e->rc_fullness = -4 * target;
   if (e->rc_fullness > 16 * target) e->rc_fullness = 16 * target;

@@ -369,7 +369,7 @@ __device__ __forceinline__ void rc_update_dev(RcState* rc, long long bits, long 
   if (target < 1) target = 1;
   const long long ref = idr ? 4 * target : target;
   const long long r = bits * 16 / ref;
-  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
+  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 1 ? -4 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
   long long full = rc->fullness + bits - target;
   if (full < -4 * target) full = -4 * target;
   if (full > 16 * target) full = 16 * target;
