@@ -27,6 +27,7 @@ struct Encoder {
   MbInfo* mbinfo = nullptr;
   int16_t* coef = nullptr;
   uint8_t* nnz = nullptr;
+  long long* mb_off = nullptr; int* mb_run = nullptr;
   uint32_t *mb_words = nullptr, *mb_nbits = nullptr, *slice_buf = nullptr, *slice_size = nullptr, *slice_rbsp = nullptr;
   long long* slice_bits = nullptr;
   int slice_words = 0;
@@ -140,6 +141,8 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMemset(e->nnz, 0, mbs * 32));
   ECK(cudaMalloc((void**)&e->mb_words, mbs * MB_WORDS * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->mb_nbits, mbs * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->mb_off, mbs * sizeof(long long)));
+  ECK(cudaMalloc((void**)&e->mb_run, mbs * sizeof(int)));
   e->slice_words = cfg->slice_rows * e->mbw * MB_WORDS + 64;
   ECK(cudaMalloc((void**)&e->slice_buf, (size_t)e->n_slices * e->slice_words * sizeof(uint32_t)));
   ECK(cudaMemset(e->slice_buf, 0, (size_t)e->n_slices * e->slice_words * sizeof(uint32_t)));
@@ -164,7 +167,7 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
 void encoder_destroy(Encoder* e) {
   if (!e) return;
   void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo, e->coef, e->nnz, e->mb_words, e->mb_nbits, e->slice_buf, e->slice_size,
-                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets};
+                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete e;
 }
@@ -182,7 +185,7 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   f.idr = idr; f.rc_mode = p->rc_mode; f.qp_fixed = p->qp_fixed; f.target_bits = p->target_bits;
   f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count;
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
-  f.mbinfo = e->mbinfo; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits;
+  f.mbinfo = e->mbinfo; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
   f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
   f.slice_bits = e->slice_bits; f.progress = e->progress; f.rc = e->rc;
   f.param_sets = e->param_sets; f.param_len = e->param_len; f.au = p->au; f.overflow = e->overflow;

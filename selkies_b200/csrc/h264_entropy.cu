@@ -6,9 +6,9 @@
 //   k_cavlc_mb    one warp per macroblock, one LANE per residual block (27 blocks): each lane sizes its
 //                 block, a warp prefix-sum places it, then it writes its codes with shared-memory atomicOr;
 //                 result: a private bit string per macroblock (+ P_Skip decision, mvd from 8.4.1.3 prediction)
-//   k_slice_bits  one block per slice: block-wide scans give every macroblock its bit offset and its
-//                 mb_skip_run; macroblock bit strings are shifted into the slice RBSP; counts the
-//                 emulation-prevention bytes the slice will need
+//   k_slice_scan  one block per slice: block-wide scans give every macroblock its bit offset and its mb_skip_run
+//   k_slice_copy  8 threads per macroblock: bit strings are shifted into the slice RBSP (atomicOr), whole picture in parallel
+//   k_slice_ep    one block per slice: counts the emulation-prevention bytes the slice will need
 //   k_pack_au     one block per slice: prefix over slice sizes, emulation prevention (parallel rule: a 03 is
 //                 inserted before byte i iff byte<=3 and the run of zero bytes before it is even and >=2),
 //                 start codes + NAL headers, AuHeader, and the frame-level rate-controller update.
@@ -197,15 +197,24 @@ constexpr int SLICE_THREADS = 256;
 
 __device__ __forceinline__ uint32_t rbsp_byte(const uint32_t* w, long long i) { return (__ldcg(&w[i >> 2]) >> (24 - 8 * (int)(i & 3))) & 255u; }
 
-__global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
-  __shared__ long long s_off[SLICE_THREADS];
-  __shared__ uint32_t s_nb[SLICE_THREADS];
-  __shared__ int s_run[SLICE_THREADS];
+__device__ __forceinline__ void or_word(uint32_t* out, long long bitpos, uint32_t v) {
+  if (!v) return;
+  const long long wi = bitpos >> 5; const int o = (int)(bitpos & 31);
+  if (o == 0) atomicOr(&out[wi], v);
+  else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
+}
+
+// ---- k_slice_scan: one block per slice.  Block-wide scans give every macroblock (a) its mb_skip_run and (b) the bit
+// offset of its first bit inside the slice RBSP.  Nothing is copied here, so a slice of many macroblock rows costs one
+// short loop iteration per 256 macroblocks.
+__global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
   __shared__ long long s_warp_sum[SLICE_THREADS / 32];
   __shared__ int s_warp_max[SLICE_THREADS / 32];
   __shared__ long long s_carry_bits;
   __shared__ int s_carry_last;      // index (within the slice) of the last non-skipped macroblock seen so far
-  __shared__ int s_red[SLICE_THREADS / 32];
+  __shared__ uint32_t s_nb[SLICE_THREADS];
+  __shared__ int s_run[SLICE_THREADS];
+  __shared__ long long s_off[SLICE_THREADS];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = s * f.slice_rows, row1 = min(f.mbh, row0 + f.slice_rows);
   const int mb0 = row0 * f.mbw, n_mb = (row1 - row0) * f.mbw;
@@ -224,9 +233,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     // I_PCM samples must start byte-aligned in the RBSP, so a macroblock's length then depends on its position:
     // chunks containing one (pathological content only) get their offsets from a serial walk below.
     const bool any_pcm = __syncthreads_or(pcm) != 0;
-    // last non-skipped index strictly before i  (max-scan)
-    int mine = skip ? -1 : i;
-    int incl_max = mine;
+    int incl_max = skip ? -1 : i;     // last non-skipped index up to and including i (max-scan)
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl_max, d); if (lane >= d) incl_max = max(incl_max, o); }
     if (lane == 31) s_warp_max[warp] = incl_max;
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     excl_max = max(excl_max, prev_max);
     const int run = i - 1 - excl_max;                      // mb_skip_run in front of macroblock i
     const int pre = (!skip && !f.idr) ? ue_len((uint32_t)run) : 0;
-    long long tot = skip ? 0 : (long long)pre + nbits;
+    const long long tot = skip ? 0 : (long long)pre + nbits;
     long long incl = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
@@ -247,9 +254,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     const long long chunk_base = s_carry_bits;
     long long woff = chunk_base;
     for (int w = 0; w < warp; w++) woff += s_warp_sum[w];
-    s_off[tid] = woff + incl - tot;
-    s_nb[tid] = skip ? 0xffffffffu : (nbits | (pcm ? 0x40000000u : 0u));
-    s_run[tid] = run;
+    long long my_off = woff + incl - tot;
+    if (any_pcm) { s_nb[tid] = skip ? 0xffffffffu : (nbits | (pcm ? 0x40000000u : 0u)); s_run[tid] = run; }
     __syncthreads();
     if (tid == SLICE_THREADS - 1) {
       long long t = chunk_base;
@@ -272,61 +278,9 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
         s_carry_bits = pos;
       }
       __syncthreads();
+      my_off = s_off[tid];
     }
-    // phase 1 — one THREAD per macroblock: mb_skip_run prefix + the first HEAD_WORDS words (covers nearly
-    // every P macroblock completely, all 256 in parallel)
-    constexpr int HEAD_WORDS = 4;
-    if (i < n_mb && !skip) {
-      long long pos = s_off[tid];
-      if (!f.idr) { GlobalSink g{out, pos}; put_ue(g, (uint32_t)run); pos = g.pos; }
-      const uint32_t* src = f.mb_words + (size_t)(mb0 + i) * MB_WORDS;
-      const int nw = min(HEAD_WORDS, (int)((nbits + 31) >> 5));
-      uint32_t v[HEAD_WORDS];
-#pragma unroll
-      for (int w = 0; w < HEAD_WORDS; w++) v[w] = w < nw ? src[w] : 0u;
-#pragma unroll
-      for (int w = 0; w < HEAD_WORDS; w++) {
-        if (v[w]) {
-          const long long p = pos + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);
-          if (o == 0) atomicOr(&out[wi], v[w]);
-          else { atomicOr(&out[wi], v[w] >> o); atomicOr(&out[wi + 1], v[w] << (32 - o)); }
-        }
-      }
-    }
-    // phase 2 — big macroblocks: warps take them round-robin, lanes stride over the remaining words
-    for (int j = warp; j < SLICE_THREADS && base + j < n_mb; j += SLICE_THREADS / 32) {
-      const uint32_t nb = s_nb[j];
-      if (nb == 0xffffffffu) continue;
-      if (nb & 0x40000000u) {     // I_PCM payload: 256 luma, 64 Cb, 64 Cr samples from the reconstruction (== source)
-        const long long pp = ((s_off[j] + (f.idr ? 0 : ue_len((uint32_t)s_run[j])) + (nb & 0x3fffffffu) + 7) & ~7LL);
-        const int mbi = mb0 + base + j, px = (mbi % f.mbw) * 16, py = (mbi / f.mbw) * 16;
-        const uint8_t* ry = f.recon; const uint8_t* ruv = f.recon + (size_t)f.cw * f.ch;
-        for (int w = lane; w < 96; w += 32) {
-          uint32_t v;
-          if (w < 64) v = __byte_perm(__ldcg(reinterpret_cast<const uint32_t*>(ry + (size_t)(py + (w >> 2)) * f.cw + px + (w & 3) * 4)), 0, 0x0123);
-          else {
-            const int k = (w - 64) & 15, comp = (w - 64) >> 4;
-            const uint2 q = __ldcg(reinterpret_cast<const uint2*>(ruv + (size_t)(py / 2 + (k >> 1)) * f.cw + px + (k & 1) * 8));
-            v = comp == 0 ? __byte_perm(q.x, q.y, 0x0246) : __byte_perm(q.x, q.y, 0x1357);
-          }
-          const long long p = pp + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);
-          if (o == 0) atomicOr(&out[wi], v);
-          else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
-        }
-        continue;
-      }
-      if (nb <= 32u * HEAD_WORDS) continue;
-      const long long pos = s_off[j] + (f.idr ? 0 : ue_len((uint32_t)s_run[j]));
-      const uint32_t* src = f.mb_words + (size_t)(mb0 + base + j) * MB_WORDS;
-      for (int w = HEAD_WORDS + lane; w < (int)((nb + 31) >> 5); w += 32) {
-        const uint32_t v = src[w];
-        if (v) {
-          const long long p = pos + 32LL * w; const long long wi = p >> 5; const int o = (int)(p & 31);
-          if (o == 0) atomicOr(&out[wi], v);
-          else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
-        }
-      }
-    }
+    if (i < n_mb) { f.mb_off[mb0 + i] = my_off; f.mb_run[mb0 + i] = run; }
     __syncthreads();
   }
   // trailing mb_skip_run, rbsp_trailing_bits
@@ -335,18 +289,69 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     if (!f.idr) { const int run = n_mb - 1 - s_carry_last; if (run > 0) put_ue(g, (uint32_t)run); }
     f.slice_bits[s] = g.pos;
     g.put(1, 1);
-    s_carry_bits = g.pos;
+    f.slice_rbsp[s] = (uint32_t)((g.pos + 7) >> 3);
   }
-  __threadfence();
-  __syncthreads();
-  const long long rbsp_bytes = (s_carry_bits + 7) >> 3;
-  // count emulation-prevention bytes (7.4.1): before byte i iff byte<=3 and zero-run before it is even and >= 2
+}
+
+// ---- k_slice_copy: COPY_LANES threads per macroblock shift its bit string (mb_skip_run prefix, CAVLC words, or the
+// 384 raw samples of an I_PCM macroblock) into the slice RBSP with atomicOr.  Fully parallel over the picture.
+constexpr int COPY_LANES = 8;
+constexpr int COPY_THREADS = 256;
+
+__global__ void __launch_bounds__(COPY_THREADS) k_slice_copy(FrameCtx f) {
+  const int gt = blockIdx.x * COPY_THREADS + threadIdx.x;
+  const int mb = gt / COPY_LANES, sub = gt % COPY_LANES;
+  if (mb >= f.mbw * f.mbh) return;
+  const uint32_t v = f.mb_nbits[mb];
+  if (v >> 31) return;                                       // P_Skip: folded into a later mb_skip_run
+  const bool pcm = ((v >> 30) & 1u) != 0;
+  const uint32_t nbits = v & 0x3fffffffu;
+  const int mby = mb / f.mbw, mbx = mb - mby * f.mbw, s = mby / f.slice_rows;
+  uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
+  long long pos = f.mb_off[mb];
+  if (!f.idr) {
+    const uint32_t run = (uint32_t)f.mb_run[mb];
+    if (sub == 0) { GlobalSink g{out, pos}; put_ue(g, run); }
+    pos += ue_len(run);
+  }
+  const uint32_t* src = f.mb_words + (size_t)mb * MB_WORDS;
+  for (int w = sub; w < (int)((nbits + 31) >> 5); w += COPY_LANES) or_word(out, pos + 32LL * w, src[w]);
+  if (pcm) {     // I_PCM payload: 256 luma, 64 Cb, 64 Cr samples from the reconstruction (== source), byte aligned
+    const long long pp = (pos + nbits + 7) & ~7LL;
+    const int px = mbx * 16, py = mby * 16;
+    const uint8_t* ry = f.recon; const uint8_t* ruv = f.recon + (size_t)f.cw * f.ch;
+    for (int w = sub; w < 96; w += COPY_LANES) {
+      uint32_t q;
+      if (w < 64) q = __byte_perm(__ldcg(reinterpret_cast<const uint32_t*>(ry + (size_t)(py + (w >> 2)) * f.cw + px + (w & 3) * 4)), 0, 0x0123);
+      else {
+        const int k = (w - 64) & 15, comp = (w - 64) >> 4;
+        const uint2 c2 = __ldcg(reinterpret_cast<const uint2*>(ruv + (size_t)(py / 2 + (k >> 1)) * f.cw + px + (k & 1) * 8));
+        q = comp == 0 ? __byte_perm(c2.x, c2.y, 0x0246) : __byte_perm(c2.x, c2.y, 0x1357);
+      }
+      or_word(out, pp + 32LL * w, q);
+    }
+  }
+}
+
+// ---- k_slice_ep: one block per slice counts the emulation-prevention bytes the slice needs (7.4.1): a 03 goes in
+// front of byte i iff byte <= 3 and the run of zero bytes before it is even and >= 2.
+__global__ void __launch_bounds__(SLICE_THREADS) k_slice_ep(FrameCtx f) {
+  __shared__ int s_red[SLICE_THREADS / 32];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
+  const long long rbsp_bytes = f.slice_rbsp[s];
   int ep = 0;
-  for (long long i = tid; i < rbsp_bytes; i += SLICE_THREADS) {
-    if (rbsp_byte(out, i) <= 3u) {
-      int z = 0;
-      while (i - 1 - z >= 0 && rbsp_byte(out, i - 1 - z) == 0u) z++;
-      if (z >= 2 && (z & 1) == 0) ep++;
+  for (long long w0 = (long long)tid * 4; w0 < rbsp_bytes; w0 += SLICE_THREADS * 4) {
+    const uint32_t word = __ldcg(&out[w0 >> 2]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long i = w0 + k;
+      const uint32_t b = (word >> (24 - 8 * k)) & 255u;
+      if (i < rbsp_bytes && b <= 3u) {
+        int z = 0;
+        while (i - 1 - z >= 0 && rbsp_byte(out, i - 1 - z) == 0u) z++;
+        if (z >= 2 && (z & 1) == 0) ep++;
+      }
     }
   }
   ep = __reduce_add_sync(FULL, ep);
@@ -356,7 +361,6 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_bits(FrameCtx f) {
     int t = 0;
     for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_red[w];
     const int start_len = (s == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of the access unit
-    f.slice_rbsp[s] = (uint32_t)rbsp_bytes;
     f.slice_size[s] = (uint32_t)(start_len + 1 + rbsp_bytes + t);
   }
 }
@@ -479,8 +483,11 @@ int launch_cavlc(const FrameCtx& f, cudaStream_t st) {
   return 1;
 }
 int launch_slice(const FrameCtx& f, cudaStream_t st) {
-  k_slice_bits<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
-  return 1;
+  const int mbs = f.mbw * f.mbh;
+  k_slice_scan<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
+  k_slice_copy<<<(mbs * COPY_LANES + COPY_THREADS - 1) / COPY_THREADS, COPY_THREADS, 0, st>>>(f);
+  k_slice_ep<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
+  return 3;
 }
 int launch_pack_cap(const FrameCtx& f, long long au_cap, cudaStream_t st) {
   k_pack_au<<<f.n_slices, PACK_THREADS, 0, st>>>(f, au_cap);
