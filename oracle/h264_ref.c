@@ -25,7 +25,7 @@
  *   - P pictures: every macroblock P_L0_16x16 (coded as P_Skip when mv == skip predictor and cbp == 0);
  *     full-pel exhaustive search dx in [-16,15], dy in [-16,16] against the previous reconstruction
  *     (coordinates clamped to the coded picture), cost = SAD + lambda(qp)*(bits_se(4dx)+bits_se(4dy)),
- *     argmin of (cost << 11 | (dy+16)*32 + (dx+16))
+ *     argmin of (cost << 11 | (dy+16)*32 + (dx+16)); the search is skipped (mv = 0) when SAD(0,0) <= 96*lambda(qp)
  *   - quantisation: |l| = (|w|*MF + f) >> (15+qp/6), f = 2^(15+qp/6)/3 intra, /6 inter, |l| clamped to 2047
  *   - constant QP inside a picture; picture QP from the frame-level rate controller below
  */
@@ -417,6 +417,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
 }
 
 /* ------------------------------------------------------------------ inter macroblock (8.4) */
+#define ME_EARLY_SAD_PER_LAMBDA 96
 static int se_bits(int v) { unsigned c = v > 0 ? 2u * v - 1 : (unsigned)(-2 * v); int len = 0; c += 1; while ((c >> len) > 1) len++; return 2 * len + 1; }
 
 static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
@@ -435,7 +436,12 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     if (x0 >= 16 && x0 + 32 <= e->cw) memcpy(win[j], rr + x0 - 16, 48);
     else for (int i = 0; i < 48; i++) win[j][i] = rr[clip3(0, e->cw - 1, x0 - 16 + i)];
   }
-  for (int dy = -16; dy <= 16; dy++)
+  /* zero-motion early termination: when the co-located block already matches to within the quantisation noise
+   * expected at this QP (SAD <= 96*lambda), the search is skipped and mv = (0,0) */
+  int sad0 = 0;
+  for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) sad0 += iabs(cy[r * 16 + c] - win[16 + r][16 + c]);
+  const int search = sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda;
+  for (int dy = -16; search && dy <= 16; dy++)
     for (int dx = -16; dx <= 15; dx++) {
       int sad = 0;
       for (int r = 0; r < 16; r++) {

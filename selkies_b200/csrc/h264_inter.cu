@@ -19,6 +19,7 @@ namespace b2v {
 
 constexpr int WIN_ROWS = 48, WIN_WORDS = 12;
 constexpr int WARPS_PER_BLOCK = 4;
+constexpr int ME_EARLY_SAD_PER_LAMBDA = 96;   // skip the search when SAD(0,0) <= 96 * lambda(qp)
 
 struct InterSm {
   MbTile t;
@@ -84,6 +85,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   }
   __syncwarp();
 
+  // ---- zero-motion early termination: co-located block within the quantisation noise of this QP ----
+  const int lambda = me_lambda[qp];
+  uint32_t best = (uint32_t)(16 * 32 + 16);      // candidate (0,0)
+  {
+    const uint32_t* w0p = &sm.win[16 + r8][4 + (c8 >> 2)];
+    const uint32_t s0 = sad4acc(*reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), w0p[0],
+                                sad4acc(*reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]), w0p[1], 0u));
+    const int sad0 = __reduce_add_sync(FULL, (int)s0);
+    if (sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda) best = 0xffffffffu;
+  }
+  if (best == 0xffffffffu) {
   // ---- exhaustive search ---------------------------------------------------------------------------
   uint32_t c[16][4];
 #pragma unroll
@@ -107,9 +119,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
         acc[dyi] = sad4acc(c[r][0], a0, sad4acc(c[r][1], a1, sad4acc(c[r][2], a2, sad4acc(c[r][3], a3, acc[dyi]))));
     }
   }
-  const int lambda = me_lambda[qp];
   const int bits_x = se_bits_c(4 * (lane - 16));
-  uint32_t best = 0xffffffffu;
 #pragma unroll
   for (int dyi = 0; dyi <= 32; dyi++) {
     const uint32_t cost = acc[dyi] + (uint32_t)(lambda * (bits_x + se_bits_c(4 * (dyi - 16))));
@@ -117,6 +127,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     best = min(best, key);
   }
   best = __reduce_min_sync(FULL, best);
+  }
   const int dyi = (best & 2047) >> 5, dxi = best & 31, dx = dxi - 16, dy = dyi - 16;
 
   // ---- prediction ------------------------------------------------------------------------------------
