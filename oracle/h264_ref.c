@@ -20,7 +20,8 @@
  *
  * Encoder decisions (the "spec" the CUDA path must match bit-for-bit):
  *   - one slice per `slice_rows` macroblock rows; deblocking disabled (disable_deblocking_filter_idc=1)
- *   - IDR pictures: Intra16x16 only; luma mode = argmin(SAD*4 + mode) over available modes
+ *   - IDR pictures: per macroblock both Intra4x4 (9 modes, per block key = (SAD + lambda*(mode==predicted ? 1 : 4))*16
+ *     + mode) and Intra16x16 are coded; the one with the smaller J = SSD + rd_lambda(qp) * luma bits is kept; I16 luma mode = argmin(SAD*4 + mode) over available modes
  *     {0 V, 1 H, 2 DC, 3 Plane}; chroma mode = argmin(SAD(Cb)+SAD(Cr))*4 + mode over {0 DC,1 H,2 V,3 Plane}
  *   - P pictures: every macroblock P_L0_16x16 (coded as P_Skip when mv == skip predictor and cbp == 0);
  *     full-pel exhaustive search dx in [-16,15], dy in [-16,16] against the previous reconstruction
@@ -83,10 +84,11 @@ typedef struct {
   int16_t coef[27][16];   /* scan-order levels: 0 luma DC (I16x16), 1..16 luma blkIdx 0..15, 17/18 chroma DC Cb/Cr, 19..22 Cb AC, 23..26 Cr AC */
   uint8_t nnz_l[16];      /* TotalCoeff per luma 4x4 block, raster y*4+x */
   uint8_t nnz_c[2][4];    /* per chroma 4x4 block (AC), raster y*2+x */
-  int8_t  type;           /* 0 I16x16, 1 P_L0_16x16, 2 I_PCM */
+  int8_t  type;           /* 0 I16x16, 1 P_L0_16x16, 2 I_PCM, 3 I_NxN (Intra4x4) */
   int8_t  i16_mode, chroma_mode;
   uint8_t cbp;            /* luma bits 0..3, chroma << 4 */
   int16_t mv[2];          /* quarter-sample units */
+  int8_t  i4_modes[16];   /* Intra4x4PredMode per 4x4 block, raster y*4+x (type 3 only) */
 } mb_t;
 
 typedef struct {
@@ -247,6 +249,7 @@ static uint8_t* plane_uv(enc_t* e, int idx) { return e->recon[idx] + (size_t)e->
 static int slice_first_row(const enc_t* e, int mby) { return (mby / e->slice_rows) * e->slice_rows; }
 static int avail_top(const enc_t* e, int mby) { return mby > slice_first_row(e, mby); }
 static void make_pcm_if_too_big(enc_t* e, mb_t* m, const uint8_t* cur_nv12, int mbx, int mby);   /* defined after the CAVLC coder */
+static void cavlc_block(bitw_t* b, const int16_t* lv, int start, int maxc, int nC);
 
 /* ------------------------------------------------------------------ chroma: shared by I and P macroblocks */
 /* cur/pred: [2][64] raster 8x8 per component.  Writes levels, nnz_c, chroma cbp; reconstructs into the frame. */
@@ -342,6 +345,114 @@ static void pred8c(int mode, const uint8_t* top, const uint8_t* left, int tl, in
 }
 static int sad_n(const uint8_t* a, const uint8_t* b, int n) { int s = 0; for (int i = 0; i < n; i++) s += iabs(a[i] - b[i]); return s; }
 
+
+/* ------------------------------------------------------------------ Intra4x4 (8.3.1) */
+/* e[0..3] = left samples bottom..top (l3,l2,l1,l0), e[4] = top-left M, e[5..12] = top samples t0..t7 (t4..t7 = top-right) */
+static int f3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
+static int f2(int a, int b) { return (a + b + 1) >> 1; }
+static int pred4_pixel(int mode, int x, int y, const uint8_t* e, int has_a, int has_b) {
+  const uint8_t* t = e + 5; /* t[-1] = M */
+#define L(i) ((i) < 0 ? e[4] : e[3 - (i)])
+  switch (mode) {
+    case 0: return t[x];
+    case 1: return L(y);
+    case 2: {
+      int s = 0;
+      if (has_a && has_b) { for (int i = 0; i < 4; i++) s += t[i] + L(i); return (s + 4) >> 3; }
+      if (has_b) { for (int i = 0; i < 4; i++) s += t[i]; return (s + 2) >> 2; }
+      if (has_a) { for (int i = 0; i < 4; i++) s += L(i); return (s + 2) >> 2; }
+      return 128;
+    }
+    case 3: return (x == 3 && y == 3) ? (t[6] + 3 * t[7] + 2) >> 2 : f3(t[x + y], t[x + y + 1], t[x + y + 2]);
+    case 4: return f3(e[4 + x - y - 1], e[4 + x - y], e[4 + x - y + 1]);
+    case 5: {
+      int z = 2 * x - y;
+      if (z >= 0 && !(z & 1)) return f2(t[x - (y >> 1) - 1], t[x - (y >> 1)]);
+      if (z >= 0) return f3(t[x - (y >> 1) - 2], t[x - (y >> 1) - 1], t[x - (y >> 1)]);
+      if (z == -1) return f3(L(0), e[4], t[0]);
+      return f3(L(y - 1), L(y - 2), L(y - 3));
+    }
+    case 6: {
+      int z = 2 * y - x;
+      if (z >= 0 && !(z & 1)) return f2(L(y - (x >> 1) - 1), L(y - (x >> 1)));
+      if (z >= 0) return f3(L(y - (x >> 1) - 2), L(y - (x >> 1) - 1), L(y - (x >> 1)));
+      if (z == -1) return f3(L(0), e[4], t[0]);
+      return f3(t[x - 1], t[x - 2], t[x - 3]);
+    }
+    case 7: return (y & 1) ? f3(t[x + (y >> 1)], t[x + (y >> 1) + 1], t[x + (y >> 1) + 2]) : f2(t[x + (y >> 1)], t[x + (y >> 1) + 1]);
+    default: {
+      int z = x + 2 * y;
+      if (z > 5) return L(3);
+      if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
+      if (z & 1) return f3(L(y + (x >> 1)), L(y + (x >> 1) + 1), L(y + (x >> 1) + 2));
+      return f2(L(y + (x >> 1)), L(y + (x >> 1) + 1));
+    }
+  }
+#undef L
+}
+static int i4_mode_ok(int mode, int has_a, int has_b, int has_d) {
+  switch (mode) {
+    case 0: case 3: case 7: return has_b;
+    case 1: case 8: return has_a;
+    case 2: return 1;
+    default: return has_a && has_b && has_d;
+  }
+}
+/* predIntra4x4PredMode (8.3.1.1) for block (bx,by) of macroblock (mbx,mby) */
+static int i4_pred_mode(const enc_t* e, int mbx, int mby, int bx, int by) {
+  const mb_t* m = &e->mbs[mby * e->mbw + mbx];
+  int ma, mb_;
+  if (bx > 0) ma = m->i4_modes[by * 4 + bx - 1];
+  else { if (mbx == 0) return 2; const mb_t* n = m - 1; ma = n->type == 3 ? n->i4_modes[by * 4 + 3] : 2; }
+  if (by > 0) mb_ = m->i4_modes[(by - 1) * 4 + bx];
+  else { if (!avail_top(e, mby)) return 2; const mb_t* n = m - e->mbw; mb_ = n->type == 3 ? n->i4_modes[12 + bx] : 2; }
+  return ma < mb_ ? ma : mb_;
+}
+/* C (top-right) availability of block (bx,by) inside the macroblock: decoded earlier in blkIdx order */
+static const uint8_t i4_tr_inside[16] = { 2,2,2,3, 1,0,1,0, 1,1,1,0, 1,0,1,0 };   /* raster; row 0: 2 = from the MB above, 3 = from the MB above-right */
+
+/* Code the luma of one macroblock as 16 Intra4x4 blocks in decoding order (reconstruction is written to the frame
+ * because each block predicts from its already reconstructed neighbours).  Returns sum(SAD + lambda*mode bits). */
+static int intra4x4_pass(enc_t* e, mb_t* m, const uint8_t cy[256], int mbx, int mby, int qp) {
+  uint8_t* ry = plane_y(e, e->cur);
+  const int x0 = mbx * 16, y0 = mby * 16, lambda = me_lambda[qp];
+  const int mb_left = mbx > 0, mb_top = avail_top(e, mby), mb_tr = mb_top && mbx + 1 < e->mbw;
+  int cost = 0;
+  for (int blk = 0; blk < 16; blk++) {
+    const int bx = blk_x[blk], by = blk_y[blk], px = x0 + bx * 4, py = y0 + by * 4;
+    const int has_a = bx > 0 || mb_left, has_b = by > 0 || mb_top;
+    const int has_d = (bx > 0 && by > 0) ? 1 : (bx > 0) ? mb_top : (by > 0) ? mb_left : (mb_left && mb_top);
+    const int trc = i4_tr_inside[by * 4 + bx];
+    const int has_c = trc == 1 ? 1 : trc == 2 ? mb_top : trc == 3 ? mb_tr : 0;
+    uint8_t ed[13];
+    memset(ed, 128, sizeof ed);
+    if (has_a) for (int i = 0; i < 4; i++) ed[3 - i] = ry[(size_t)(py + i) * e->cw + px - 1];
+    if (has_d) ed[4] = ry[(size_t)(py - 1) * e->cw + px - 1];
+    if (has_b) {
+      for (int i = 0; i < 4; i++) ed[5 + i] = ry[(size_t)(py - 1) * e->cw + px + i];
+      for (int i = 4; i < 8; i++) ed[5 + i] = has_c ? ry[(size_t)(py - 1) * e->cw + px + i] : ed[8];   /* 8.3.1.2: replicate p[3,-1] */
+    }
+    const int pm = i4_pred_mode(e, mbx, mby, bx, by);
+    int best_key = 1 << 30, best_mode = 2; uint8_t best_pred[16];
+    for (int mode = 0; mode < 9; mode++) {
+      if (!i4_mode_ok(mode, has_a, has_b, has_d)) continue;
+      uint8_t pr[16]; int sad = 0;
+      for (int i = 0; i < 16; i++) { pr[i] = (uint8_t)pred4_pixel(mode, i & 3, i >> 2, ed, has_a, has_b); sad += iabs(cy[(by * 4 + (i >> 2)) * 16 + bx * 4 + (i & 3)] - pr[i]); }
+      int key = (sad + lambda * (mode == pm ? 1 : 4)) * 16 + mode;
+      if (key < best_key) { best_key = key; best_mode = mode; memcpy(best_pred, pr, 16); }
+    }
+    m->i4_modes[by * 4 + bx] = (int8_t)best_mode;
+    cost += best_key >> 4;
+    int res[16], dummy, resid[16];
+    for (int i = 0; i < 16; i++) res[i] = cy[(by * 4 + (i >> 2)) * 16 + bx * 4 + (i & 3)] - best_pred[i];
+    tq4x4(res, qp, 1, 0, m->coef[1 + blk], &dummy);
+    m->nnz_l[by * 4 + bx] = (uint8_t)count_nz(m->coef[1 + blk], 0, 16);
+    recon4x4(m->coef[1 + blk], qp, 0, 0, resid);
+    for (int i = 0; i < 16; i++) ry[(size_t)(py + (i >> 2)) * e->cw + px + (i & 3)] = (uint8_t)clip1(best_pred[i] + resid[i]);
+  }
+  return cost;
+}
+
 static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
   mb_t* m = &e->mbs[mby * e->mbw + mbx];
   memset(m, 0, sizeof *m);
@@ -379,6 +490,13 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     int key = (sad_n(cc[0], cpred[0], 64) + sad_n(cc[1], cpred[1], 64)) * 4 + mode;
     if (key < best_key) { best_key = key; m->chroma_mode = (int8_t)mode; memcpy(best_cpred, cpred, 128); }
   }
+  /* Intra4x4 candidate: run completely first (it needs its own reconstruction block by block) and saved; the
+   * Intra16x16 coding below then overwrites frame and macroblock state, and the rate-distortion comparison at the
+   * end restores the 4x4 result if it wins. */
+  intra4x4_pass(e, m, cy, mbx, mby, qp);
+  mb_t m4 = *m;
+  uint8_t rec4[256];
+  for (int r = 0; r < 16; r++) memcpy(rec4 + 16 * r, ry + (size_t)(mby * 16 + r) * e->cw + mbx * 16, 16);
   /* luma: 16 blocks, DC separated (8.5.2) */
   int dcs[16], any_ac = 0;
   for (int b = 0; b < 16; b++) {
@@ -409,6 +527,42 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     for (int i = 0; i < 16; i++) {
       int y = by + (i >> 2), x = bx + (i & 3);
       ry[(size_t)(mby * 16 + y) * e->cw + mbx * 16 + x] = (uint8_t)clip1(best_pred[y * 16 + x] + resid[i]);
+    }
+  }
+  /* mode decision J = SSD + lambda_rd * bits over the luma (chroma is coded identically either way) */
+  {
+    int64_t d16 = 0, d4 = 0;
+    for (int r = 0; r < 16; r++)
+      for (int c = 0; c < 16; c++) {
+        int a = cy[r * 16 + c] - ry[(size_t)(mby * 16 + r) * e->cw + mbx * 16 + c], b4 = cy[r * 16 + c] - rec4[r * 16 + c];
+        d16 += a * a; d4 += b4 * b4;
+      }
+    bitw_t b; bw_init(&b);
+    cavlc_block(&b, m->coef[0], 0, 16, -2);
+    if (any_ac) for (int blk = 0; blk < 16; blk++) cavlc_block(&b, m->coef[1 + blk], 1, 15, -2);
+    int bits16 = 8 + (int)bw_bits(&b);
+    bw_free(&b); bw_init(&b);
+    int cbp4 = 0, bits4 = 8;
+    for (int blk = 0; blk < 16; blk++) if (m4.nnz_l[blk_y[blk] * 4 + blk_x[blk]]) cbp4 |= 1 << (blk >> 2);
+    for (int blk = 0; blk < 16; blk++) {
+      if (cbp4 & (1 << (blk >> 2))) cavlc_block(&b, m4.coef[1 + blk], 0, 16, -2);
+      /* the mode bits are recomputed against the I4 state, which is what the entropy coder will see */
+    }
+    bits4 += (int)bw_bits(&b);
+    bw_free(&b);
+    { mb_t keep = *m; *m = m4;      /* i4_pred_mode() reads the macroblock's own modes */
+      for (int blk = 0; blk < 16; blk++) bits4 += m4.i4_modes[blk_y[blk] * 4 + blk_x[blk]] == i4_pred_mode(e, mbx, mby, blk_x[blk], blk_y[blk]) ? 1 : 4;
+      *m = keep; }
+    const int64_t l2 = rd_lambda[qp];
+    if (d4 + l2 * bits4 < d16 + l2 * bits16 && !getenv("B2V_REF_NO_I4")) {
+      int8_t cm = m->chroma_mode;
+      *m = m4; m->type = 3; m->chroma_mode = cm;
+      for (int r = 0; r < 16; r++) memcpy(ry + (size_t)(mby * 16 + r) * e->cw + mbx * 16, rec4 + 16 * r, 16);
+      any_ac = 0;
+      int cbp_c4 = code_chroma(e, m, mbx, mby, qp, 1, cc, best_cpred);
+      m->cbp = (uint8_t)(cbp4 | (cbp_c4 << 4));
+      make_pcm_if_too_big(e, m, cur_nv12, mbx, mby);
+      return;
     }
   }
   int cbp_c = code_chroma(e, m, mbx, mby, qp, 1, cc, best_cpred);
@@ -612,6 +766,7 @@ static void mv_pred_skip(const enc_t* e, int mbx, int mby, int out[2]) {
 static int mb_bits_estimate(const mb_t* m) {
   bitw_t b; bw_init(&b);
   if (m->type == 0) cavlc_block(&b, m->coef[0], 0, 16, -2);
+  if (m->type == 3) bw_put(&b, 32, 0), bw_put(&b, 16, 0);   /* Intra4x4: up to 64 bits of prediction modes -> 96-bit header budget */
   for (int blk = 0; blk < 16; blk++) {
     if (!(m->cbp & (1 << (blk >> 2)))) continue;
     if (m->type == 0) cavlc_block(&b, m->coef[1 + blk], 1, 15, -2); else cavlc_block(&b, m->coef[1 + blk], 0, 16, -2);
@@ -693,6 +848,19 @@ static size_t code_slice(enc_t* e, int s, int idr, int qp, uint8_t* skip, uint8_
         for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) bw_put(&b, 8, ry[(size_t)(mby * 16 + r) * e->cw + mbx * 16 + c]);
         for (int k = 0; k < 2; k++)
           for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) bw_put(&b, 8, ruv[(size_t)(mby * 8 + r) * e->cw + (mbx * 8 + c) * 2 + k]);
+        continue;
+      }
+      if (m->type == 3) {                       /* I_NxN with Intra4x4 (7.3.5, 7.3.5.1) */
+        bw_ue(&b, idr ? 0 : 5);
+        for (int blk = 0; blk < 16; blk++) {
+          int bx = blk_x[blk], by = blk_y[blk], mode = m->i4_modes[by * 4 + bx], pm = i4_pred_mode(e, mbx, mby, bx, by);
+          if (mode == pm) bw_put(&b, 1, 1);
+          else { bw_put(&b, 1, 0); bw_put(&b, 3, mode < pm ? mode : mode - 1); }
+        }
+        bw_ue(&b, m->chroma_mode);
+        bw_ue(&b, cbp_to_codenum_intra[m->cbp]);
+        if (m->cbp) bw_se(&b, 0);
+        write_residual(e, &b, skip, m, mbx, mby);
         continue;
       }
       if (m->type == 0) {

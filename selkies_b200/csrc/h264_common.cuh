@@ -11,7 +11,7 @@
 
 namespace b2v {
 
-constexpr int MB_I16 = 0, MB_P16 = 1, MB_PCM = 2;
+constexpr int MB_I16 = 0, MB_P16 = 1, MB_PCM = 2, MB_I4 = 3;
 constexpr int COEF_BLOCKS = 27;            // 0 luma DC | 1..16 luma | 17,18 chroma DC | 19..26 chroma AC
 constexpr int MB_BITS_LIMIT = 3200;         // A.3.1: bits of macroblock_layer() per macroblock
 constexpr int MB_WORDS = 128;              // per-macroblock bit scratch: 128 x u32 = 4096 bits
@@ -41,6 +41,7 @@ struct FrameCtx {          // everything a kernel needs about the picture being 
   const uint8_t* ref;      // previous reconstruction (NV12)
   uint8_t* recon;          // reconstruction being written
   MbInfo* mbinfo;
+  uint8_t* i4modes;        // [mbs][16] Intra4x4PredMode per block (raster), valid for MB_I4
   int16_t* coef;           // [mbs][27][16]
   uint8_t* nnz;            // [mbs][32]: 0..15 luma raster, 16..19 Cb, 20..23 Cr
   uint32_t* mb_words;      // [mbs][MB_WORDS]
@@ -181,7 +182,7 @@ struct MbTile {
 // nnz and the reconstruction into the tile (rec_y / rec_uv), returns cbp (all lanes).
 //   INTRA16: luma DC separated + Hadamard (8.5.2 / 8.5.10), cbp luma is 0 or 15.
 template <bool INTRA16>
-__device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t* coef_mb, uint8_t* nnz_mb) {
+__device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t* coef_mb, uint8_t* nnz_mb, int& luma_bits, int& chroma_bits) {
   const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
   const int qpc = chroma_qp_tab[qp];
   const QuantParams q = make_quant(is_chroma ? qpc : qp, INTRA16);
@@ -310,9 +311,8 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
   if (INTRA16) cbp_l = (nzmask & 0xffffu) ? 15 : 0;
   else cbp_l = ((nzmask & 0x000fu) ? 1 : 0) | ((nzmask & 0x00f0u) ? 2 : 0) | ((nzmask & 0x0f00u) ? 4 : 0) | ((nzmask & 0xf000u) ? 8 : 0);
   int cbp_c = (nzmask & 0xff0000u) ? 2 : (dcmask ? 1 : 0);
-  // ---- I_PCM decision: upper bound of macroblock_layer() bits = exact CAVLC size of every coded
-  // block with the longest coeff_token of the four nC tables + 48 header bits; above the 3200-bit limit of A.3.1
-  // the macroblock is sent raw and its reconstruction becomes the source samples. -------------------------------
+  // ---- size estimate for the I_PCM decision and the intra mode decision: exact CAVLC size of every
+  // coded block with the longest coeff_token of the four nC tables ----------------------------------------------
   __syncwarp();
   {
     bool coded = false; int start = 0, maxc = 16, nC = NC_WORST;
@@ -322,16 +322,18 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
     else if (lane <= 26) { coded = cbp_c == 2; start = 1; maxc = 15; }
     CountSink cs;
     if (coded) cavlc_block(cs, &t.lvs[lane][start], maxc, nC);
-    const int est = 48 + __reduce_add_sync(FULL, cs.n);
-    if (est > MB_BITS_LIMIT) {
-      const int r8 = lane >> 1, c8 = (lane & 1) * 8;
-      *reinterpret_cast<uint2*>(&t.rec_y[r8][c8]) = *reinterpret_cast<const uint2*>(&t.cur_y[r8][c8]);
-      if (lane < 16) *reinterpret_cast<uint2*>(&t.rec_uv[r8][c8]) = *reinterpret_cast<const uint2*>(&t.cur_uv[r8][c8]);
-      if (lane < 24) nnz_mb[lane] = 16;
-      return -1;
-    }
+    luma_bits = __reduce_add_sync(FULL, lane <= 16 ? cs.n : 0);
+    chroma_bits = __reduce_add_sync(FULL, lane > 16 ? cs.n : 0);
   }
   return cbp_l | (cbp_c << 4);
+}
+
+// I_PCM: the reconstruction becomes the source samples, every block counts 16 coefficients for its neighbours' nC.
+__device__ __forceinline__ void apply_pcm(MbTile& t, int lane, uint8_t* nnz_mb) {
+  const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+  *reinterpret_cast<uint2*>(&t.rec_y[r8][c8]) = *reinterpret_cast<const uint2*>(&t.cur_y[r8][c8]);
+  if (lane < 16) *reinterpret_cast<uint2*>(&t.rec_uv[r8][c8]) = *reinterpret_cast<const uint2*>(&t.cur_uv[r8][c8]);
+  if (lane < 24) nnz_mb[lane] = 16;
 }
 
 }  // namespace b2v

@@ -25,6 +25,7 @@ struct Encoder {
   uint8_t* recon[2] = {nullptr, nullptr};
   int cur = 0;
   MbInfo* mbinfo = nullptr;
+  uint8_t* i4modes = nullptr;
   int16_t* coef = nullptr;
   uint8_t* nnz = nullptr;
   long long* mb_off = nullptr; int* mb_run = nullptr;
@@ -135,6 +136,8 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMemset(e->recon[0], 0, fb));
   ECK(cudaMemset(e->recon[1], 0, fb));
   ECK(cudaMalloc((void**)&e->mbinfo, mbs * sizeof(MbInfo)));
+  ECK(cudaMalloc((void**)&e->i4modes, mbs * 16));
+  ECK(cudaMemset(e->i4modes, 2, mbs * 16));
   ECK(cudaMalloc((void**)&e->coef, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
   ECK(cudaMemset(e->coef, 0, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
   ECK(cudaMalloc((void**)&e->nnz, mbs * 32));
@@ -167,7 +170,7 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
 void encoder_destroy(Encoder* e) {
   if (!e) return;
   void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo, e->coef, e->nnz, e->mb_words, e->mb_nbits, e->slice_buf, e->slice_size,
-                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run};
+                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete e;
 }
@@ -185,7 +188,7 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   f.idr = idr; f.rc_mode = p->rc_mode; f.qp_fixed = p->qp_fixed; f.target_bits = p->target_bits;
   f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count;
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
-  f.mbinfo = e->mbinfo; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
+  f.mbinfo = e->mbinfo; f.i4modes = e->i4modes; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
   f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
   f.slice_bits = e->slice_bits; f.progress = e->progress; f.rc = e->rc;
   f.param_sets = e->param_sets; f.param_len = e->param_len; f.au = p->au; f.overflow = e->overflow;

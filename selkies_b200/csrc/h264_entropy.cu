@@ -52,6 +52,27 @@ __device__ __forceinline__ void mv_pred_skip(const MvCtx& m, int& px, int& py) {
   mv_pred16(m, px, py);
 }
 
+// I_NxN macroblock header (7.3.5, 7.3.5.1): mb_type, 16 x (prev_intra4x4_pred_mode_flag [rem_intra4x4_pred_mode]),
+// intra_chroma_pred_mode, coded_block_pattern (intra me(v) mapping), mb_qp_delta
+template <class S>
+__device__ __forceinline__ void mb_header_i4(S& h, const FrameCtx& f, const MbInfo& mi, int mb, int mbx, int mby) {
+  put_ue(h, f.idr ? 0u : 5u);
+  const uint8_t* own = f.i4modes + (size_t)mb * 16;
+  const bool availA = mbx > 0, availB = top_in_slice(f, mby);
+  const bool a_i4 = availA && f.mbinfo[mb - 1].type == MB_I4, b_i4 = availB && f.mbinfo[mb - f.mbw].type == MB_I4;
+  for (int blk = 0; blk < 16; blk++) {
+    const int bx = blk_x[blk], by = blk_y[blk], mode = own[by * 4 + bx];
+    const int ma = bx > 0 ? (int)own[by * 4 + bx - 1] : !availA ? -1 : a_i4 ? (int)f.i4modes[(size_t)(mb - 1) * 16 + by * 4 + 3] : 2;
+    const int mbm = by > 0 ? (int)own[(by - 1) * 4 + bx] : !availB ? -1 : b_i4 ? (int)f.i4modes[(size_t)(mb - f.mbw) * 16 + 12 + bx] : 2;
+    const int pm = (ma < 0 || mbm < 0) ? 2 : min(ma, mbm);
+    if (mode == pm) h.put(1, 1);
+    else { h.put(1, 0); h.put(3, (uint32_t)(mode < pm ? mode : mode - 1)); }
+  }
+  put_ue(h, mi.chroma_mode);
+  put_ue(h, cbp_to_codenum_intra[mi.cbp]);
+  if (mi.cbp) put_se(h, 0);
+}
+
 // ------------------------------------------------------------------------------------------------ k_cavlc_mb
 constexpr int CAVLC_WARPS = 4;
 
@@ -133,7 +154,8 @@ __global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
   int hdr_bits;
   {
     CountSink h;
-    if (mi.type == MB_I16) {
+    if (mi.type == MB_I4) mb_header_i4(h, f, mi, mb, mbx, mby);
+    else if (mi.type == MB_I16) {
       const int tcode = 1 + mi.i16_mode + 4 * cbp_c + (cbp_l ? 12 : 0);
       put_ue(h, (uint32_t)(f.idr ? tcode : tcode + 5)); put_ue(h, mi.chroma_mode); put_se(h, 0);
     } else {
@@ -151,7 +173,8 @@ __global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
   // ---- pass 2: write -----------------------------------------------------------------------------------
   if (lane == 0) {
     SmemSink h{words, 0, MB_WORDS * 32};
-    if (mi.type == MB_I16) {
+    if (mi.type == MB_I4) mb_header_i4(h, f, mi, mb, mbx, mby);
+    else if (mi.type == MB_I16) {
       const int tcode = 1 + mi.i16_mode + 4 * cbp_c + (cbp_l ? 12 : 0);
       put_ue(h, (uint32_t)(f.idr ? tcode : tcode + 5)); put_ue(h, mi.chroma_mode); put_se(h, 0);
     } else {

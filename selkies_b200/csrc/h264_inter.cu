@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   __syncwarp();
 
   // ---- residual + reconstruction ------------------------------------------------------------------------
-  const int cbp = transform_mb<false>(t, lane, qp, f.coef + (size_t)mb * COEF_BLOCKS * 16, f.nnz + (size_t)mb * 32);
+  int luma_bits, chroma_bits;
+  int cbp = transform_mb<false>(t, lane, qp, f.coef + (size_t)mb * COEF_BLOCKS * 16, f.nnz + (size_t)mb * 32, luma_bits, chroma_bits);
+  if (48 + luma_bits + chroma_bits > MB_BITS_LIMIT) { apply_pcm(t, lane, f.nnz + (size_t)mb * 32); cbp = -1; }   // A.3.1: send raw
   __syncwarp();
   {
     const uint2 v = *reinterpret_cast<const uint2*>(&t.rec_y[r8][c8]);

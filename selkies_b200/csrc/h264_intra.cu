@@ -1,10 +1,18 @@
-// h264_intra.cu — IDR pictures: Intra16x16 macroblocks (ITU-T H.264 8.3.3 luma, 8.3.4 chroma).
+// h264_intra.cu — IDR pictures: Intra4x4 / Intra16x16 macroblocks (ITU-T H.264 8.3.1, 8.3.3 luma; 8.3.4 chroma).
 //
 // One warp per macroblock ROW: intra prediction needs the reconstructed left neighbour, so the
 // macroblocks of a row are a serial chain; rows of the same slice additionally wait for the row above
-// (wavefront, one macroblock of lag) through a progress counter in global memory.  With the default
-// slice_rows = 1 every row is its own slice and all rows run fully in parallel.
-// Encoder decisions: DESIGN.md §5.2; CPU restatement: oracle/h264_ref.c encode_intra_mb().
+// (wavefront, two macroblocks of lag because Intra4x4 reads the above-right samples) through a progress
+// counter in global memory.  With the default slice_rows = 1 every row is its own slice and all rows run in parallel.
+//
+// Per macroblock the warp codes the luma BOTH ways and keeps the better one:
+//   Intra4x4   16 blocks in decoding order; per block the 32 lanes evaluate 8 modes x 4 rows (+ horizontal-up)
+//              in parallel, key = (SAD + lambda*(mode == predicted ? 1 : 4))*16 + mode, then lanes 0..15 hold one
+//              residual sample each and run the 4x4 transform / quantisation / reconstruction with warp shuffles
+//   Intra16x16 luma mode = argmin(SAD*4 + mode); transform_mb<true> (one lane per 4x4 block, DC Hadamard)
+//   decision   J = SSD + rd_lambda(qp) * luma bits (exact CAVLC size with the longest coeff_token); smaller J wins.
+// Chroma: mode = argmin((SAD Cb + SAD Cr)*4 + mode).  Encoder decisions: DESIGN.md §5.2; CPU restatement:
+// oracle/h264_ref.c encode_intra_mb(), intra4x4_pass().
 #include "h264_common.cuh"
 #include "h264_kernels.h"
 
@@ -13,28 +21,108 @@ namespace b2v {
 __device__ __forceinline__ uint32_t rep4(int v) { return (uint32_t)v * 0x01010101u; }
 
 struct IntraNb {
-  uint8_t top_y[16]; uint8_t left_y[16];
+  uint8_t top_y[20];                         // 16 samples above the macroblock + 4 above-right
+  uint8_t left_y[16];
   uint8_t top_uv[16]; uint8_t left_uv[16];   // interleaved Cb,Cr: [x*2+c] / [y*2+c]
   int tl_y, tl_u, tl_v;
   int cdc[8];                                // chroma DC prediction per (comp*4 + blk)
+  uint8_t left_modes[4];                     // Intra4x4PredMode of the left macroblock's right column (2 if it is not I4x4)
+  uint8_t top_modes[4];                      // ... of the above macroblock's bottom row
 };
+
+struct I4State {
+  uint8_t rec[16][16];
+  int16_t lv[16][16];                        // [blkIdx][scan position]
+  uint8_t nnz[16];                           // raster block position
+  uint8_t modes[16];                         // raster block position
+  uint8_t ed[16];                            // edge samples of the current block: l3 l2 l1 l0 | M | t0..t7
+};
+
+__device__ __forceinline__ int f3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
+__device__ __forceinline__ int f2(int a, int b) { return (a + b + 1) >> 1; }
+
+// 8.3.1.2.1-9; e[0..3] = left samples bottom..top, e[4] = top-left, e[5..12] = top + top-right
+__device__ __forceinline__ int pred4_pixel(int mode, int x, int y, const uint8_t* e, bool has_a, bool has_b) {
+  const uint8_t* t = e + 5;
+#define L4(i) ((i) < 0 ? (int)e[4] : (int)e[3 - (i)])
+  switch (mode) {
+    case 0: return t[x];
+    case 1: return L4(y);
+    case 2: {
+      const int st = t[0] + t[1] + t[2] + t[3], sl = e[0] + e[1] + e[2] + e[3];
+      return has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128;
+    }
+    case 3: return (x == 3 && y == 3) ? (t[6] + 3 * t[7] + 2) >> 2 : f3(t[x + y], t[x + y + 1], t[x + y + 2]);
+    case 4: return f3(e[4 + x - y - 1], e[4 + x - y], e[4 + x - y + 1]);
+    case 5: {
+      const int z = 2 * x - y;
+      if (z >= 0 && !(z & 1)) return f2(t[x - (y >> 1) - 1], t[x - (y >> 1)]);
+      if (z >= 0) return f3(t[x - (y >> 1) - 2], t[x - (y >> 1) - 1], t[x - (y >> 1)]);
+      if (z == -1) return f3(L4(0), e[4], t[0]);
+      return f3(L4(y - 1), L4(y - 2), L4(y - 3));
+    }
+    case 6: {
+      const int z = 2 * y - x;
+      if (z >= 0 && !(z & 1)) return f2(L4(y - (x >> 1) - 1), L4(y - (x >> 1)));
+      if (z >= 0) return f3(L4(y - (x >> 1) - 2), L4(y - (x >> 1) - 1), L4(y - (x >> 1)));
+      if (z == -1) return f3(L4(0), e[4], t[0]);
+      return f3(t[x - 1], t[x - 2], t[x - 3]);
+    }
+    case 7: return (y & 1) ? f3(t[x + (y >> 1)], t[x + (y >> 1) + 1], t[x + (y >> 1) + 2]) : f2(t[x + (y >> 1)], t[x + (y >> 1) + 1]);
+    default: {
+      const int z = x + 2 * y;
+      if (z > 5) return L4(3);
+      if (z == 5) return (L4(2) + 3 * L4(3) + 2) >> 2;
+      if (z & 1) return f3(L4(y + (x >> 1)), L4(y + (x >> 1) + 1), L4(y + (x >> 1) + 2));
+      return f2(L4(y + (x >> 1)), L4(y + (x >> 1) + 1));
+    }
+  }
+#undef L4
+}
+__device__ __forceinline__ bool i4_mode_ok(int mode, bool has_a, bool has_b, bool has_d) {
+  switch (mode) {
+    case 0: case 3: case 7: return has_b;
+    case 1: case 8: return has_a;
+    case 2: return true;
+    default: return has_a && has_b && has_d;
+  }
+}
+// above-right availability of block (bx,by) inside the macroblock, raster: 1 inside, 2 from the MB above, 3 above-right MB
+__device__ const uint8_t i4_tr_inside[16] = { 2,2,2,3, 1,0,1,0, 1,1,1,0, 1,0,1,0 };
+__device__ const uint8_t inv_zigzag4x4[16] = { 0,1,5,6, 2,4,7,12, 3,8,11,13, 9,10,14,15 };   // raster -> scan position
+
+// one 1-D stage of the forward / inverse core transform for the element `k` of (a,b,c,d)
+__device__ __forceinline__ int fwd1(int k, int a, int b, int c, int d) {
+  return k == 0 ? a + b + c + d : k == 1 ? 2 * (a - d) + (b - c) : k == 2 ? (a + d) - (b + c) : (a - d) - 2 * (b - c);
+}
+__device__ __forceinline__ int inv1(int k, int p0, int p1, int p2, int p3) {
+  const int e0 = p0 + p2, e1 = p0 - p2, e2 = (p1 >> 1) - p3, e3 = p1 + (p3 >> 1);
+  return k == 0 ? e0 + e3 : k == 1 ? e1 + e2 : k == 2 ? e1 - e2 : e0 - e3;
+}
 
 __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
   __shared__ __align__(16) MbTile t;
   __shared__ __align__(16) IntraNb nb;
+  __shared__ __align__(16) I4State i4;
   const int lane = threadIdx.x, mby = blockIdx.x;
   const int qp = frame_qp(f);
+  const int lambda = me_lambda[qp];
   const bool has_top = top_in_slice(f, mby);
+  const bool signal_progress = f.slice_rows > 1 && mby + 1 < f.mbh && top_in_slice(f, mby + 1);
   const size_t ysz = (size_t)f.cw * f.ch;
   const uint8_t* cur_y = f.cur; const uint8_t* cur_uv = f.cur + ysz;
   uint8_t* rec_y = f.recon; uint8_t* rec_uv = f.recon + ysz;
   const int r8 = lane >> 1, c8 = (lane & 1) * 8;            // this lane's 8 luma pixels
   const int rc4 = lane >> 2, cc4 = (lane & 3) * 4;          // this lane's 4 interleaved chroma bytes
+  const QuantParams q4 = make_quant(qp, true);
+  if (lane < 4) nb.left_modes[lane] = 2;
 
   for (int mbx = 0; mbx < f.mbw; mbx++) {
+    const int mb = mby * f.mbw + mbx;
     const bool has_left = mbx > 0;
-    if (has_top) {       // wavefront: the row above must have finished macroblock mbx
-      if (lane == 0) { while (*((volatile int*)&f.progress[mby - 1]) < mbx + 1) { } __threadfence(); }
+    const bool has_tr = has_top && mbx + 1 < f.mbw;
+    if (has_top) {       // wavefront: the row above must have finished macroblock mbx+1 (above-right samples)
+      if (lane == 0) { const int need = min(mbx + 2, f.mbw); while (*((volatile int*)&f.progress[mby - 1]) < need) { } __threadfence(); }
       __syncwarp();
     }
     // ---- load current macroblock and neighbours --------------------------------------------------
@@ -48,6 +136,13 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       if (has_top) {
         if (lane < 16) nb.top_y[lane] = __ldcg(rec_y + (size_t)(mby * 16 - 1) * f.cw + mbx * 16 + lane);
         else nb.top_uv[lane - 16] = __ldcg(rec_uv + (size_t)(mby * 8 - 1) * f.cw + mbx * 16 + (lane - 16));
+        if (lane < 4) {
+          nb.top_y[16 + lane] = has_tr ? __ldcg(rec_y + (size_t)(mby * 16 - 1) * f.cw + mbx * 16 + 16 + lane) : (uint8_t)128;
+          // written by the block of the row above during this launch: read through L2, not the (incoherent) L1
+          const uint2 tm = __ldcg(reinterpret_cast<const uint2*>(&f.mbinfo[mb - f.mbw]));
+          const int ttype = tm.y & 255;
+          nb.top_modes[lane] = ttype == MB_I4 ? __ldcg(&f.i4modes[(size_t)(mb - f.mbw) * 16 + 12 + lane]) : (uint8_t)2;
+        }
         if (has_left && lane == 0) {
           nb.tl_y = __ldcg(rec_y + (size_t)(mby * 16 - 1) * f.cw + mbx * 16 - 1);
           nb.tl_u = __ldcg(rec_uv + (size_t)(mby * 8 - 1) * f.cw + mbx * 16 - 2);
@@ -68,7 +163,7 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       else dc = has_left ? (sl + 2) >> 2 : has_top ? (st + 2) >> 2 : 128;
       nb.cdc[lane] = dc;
     }
-    // ---- luma mode decision: key = SAD*4 + mode over available modes -------------------------------
+    // ---- Intra16x16 luma mode decision: key = SAD*4 + mode over available modes -------------------
     const uint32_t cy0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]);
     const uint32_t cy1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
     int sum_t = 0, sum_l = 0, H = 0, V = 0;
@@ -137,10 +232,122 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
     }
     *reinterpret_cast<uint32_t*>(&t.pred_uv[rc4][cc4]) = cbest == 0 ? qd : cbest == 1 ? qh : cbest == 2 ? qv : qp_;
     __syncwarp();
-    // ---- transform / quantise / reconstruct ---------------------------------------------------------
-    const int mb = mby * f.mbw + mbx;
-    const int cbp = transform_mb<true>(t, lane, qp, f.coef + (size_t)mb * COEF_BLOCKS * 16, f.nnz + (size_t)mb * 32);
+
+    // ---- Intra4x4 candidate: 16 blocks in decoding order ----------------------------------------------
+    int mode_bits4 = 0;
+    for (int blk = 0; blk < 16; blk++) {
+      const int bx = blk_x[blk], by = blk_y[blk];
+      const bool has_a = bx > 0 || has_left, has_b = by > 0 || has_top;
+      const bool has_d = (bx > 0 && by > 0) ? true : bx > 0 ? has_top : by > 0 ? has_left : (has_left && has_top);
+      const int trc = i4_tr_inside[by * 4 + bx];
+      const bool has_c = trc == 1 ? true : trc == 2 ? has_top : trc == 3 ? has_tr : false;
+      if (lane < 13) {        // edge samples of this block
+        int v = 128;
+        if (lane < 4) {
+          const int k = 3 - lane;
+          if (has_a) v = bx > 0 ? i4.rec[by * 4 + k][bx * 4 - 1] : nb.left_y[by * 4 + k];
+        } else if (lane == 4) {
+          if (has_d) v = (bx > 0 && by > 0) ? (int)i4.rec[by * 4 - 1][bx * 4 - 1] : bx > 0 ? (int)nb.top_y[bx * 4 - 1] : by > 0 ? (int)nb.left_y[by * 4 - 1] : nb.tl_y;
+        } else if (has_b) {
+          const int j = (lane - 5 < 4 || has_c) ? lane - 5 : 3;        // 8.3.1.2: missing above-right samples repeat p[3,-1]
+          v = by > 0 ? i4.rec[by * 4 - 1][bx * 4 + j] : nb.top_y[bx * 4 + j];
+        }
+        i4.ed[lane] = (uint8_t)v;
+      }
+      __syncwarp();
+      // predicted mode (8.3.1.1)
+      int pm;
+      {
+        const int ma = bx > 0 ? (int)i4.modes[by * 4 + bx - 1] : has_left ? (int)nb.left_modes[by] : -1;
+        const int mb_ = by > 0 ? (int)i4.modes[(by - 1) * 4 + bx] : has_top ? (int)nb.top_modes[bx] : -1;
+        pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
+      }
+      // modes 0..7: lane = mode*4 + row; mode 8: every group of four lanes evaluates it as well
+      const int m = lane >> 2, y = lane & 3;
+      const uint32_t crow = *reinterpret_cast<const uint32_t*>(&t.cur_y[by * 4 + y][bx * 4]);
+      int sad_m = 0, sad_hu = 0;
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        const int c = (crow >> (8 * x)) & 255;
+        sad_m += abs(c - pred4_pixel(m, x, y, i4.ed, has_a, has_b));
+        sad_hu += abs(c - pred4_pixel(8, x, y, i4.ed, has_a, has_b));
+      }
+      sad_m += __shfl_xor_sync(FULL, sad_m, 1); sad_m += __shfl_xor_sync(FULL, sad_m, 2);
+      sad_hu += __shfl_xor_sync(FULL, sad_hu, 1); sad_hu += __shfl_xor_sync(FULL, sad_hu, 2);
+      uint32_t key = 0xffffffffu;
+      if (i4_mode_ok(m, has_a, has_b, has_d)) key = (uint32_t)((sad_m + lambda * (m == pm ? 1 : 4)) * 16 + m);
+      if (has_a) key = min(key, (uint32_t)((sad_hu + lambda * (8 == pm ? 1 : 4)) * 16 + 8));
+      key = __reduce_min_sync(FULL, key);
+      const int mode = key & 15;
+      mode_bits4 += mode == pm ? 1 : 4;
+      // lanes 0..15: one sample each; transform / quantise / reconstruct with shuffles (lanes 16..31 mirror 0..15)
+      const int px = lane & 3, py = (lane >> 2) & 3, rpos = py * 4 + px;
+      const int pred = pred4_pixel(mode, px, py, i4.ed, has_a, has_b);
+      const int res = (int)t.cur_y[by * 4 + py][bx * 4 + px] - pred;
+      const int rowb = lane & ~3, colb = (lane & 16) | px;
+      int v = fwd1(px, __shfl_sync(FULL, res, rowb), __shfl_sync(FULL, res, rowb + 1), __shfl_sync(FULL, res, rowb + 2), __shfl_sync(FULL, res, rowb + 3));
+      v = fwd1(py, __shfl_sync(FULL, v, colb), __shfl_sync(FULL, v, colb + 4), __shfl_sync(FULL, v, colb + 8), __shfl_sync(FULL, v, colb + 12));
+      const int cls = pos_class(rpos);
+      const int level = quant1(v, q4.mf[cls], q4.f, q4.qbits);
+      const unsigned nzm = __ballot_sync(FULL, level != 0) & 0xffffu;
+      if (lane < 16) i4.lv[blk][inv_zigzag4x4[rpos]] = (int16_t)level;
+      int d = (level * q4.dq[cls]) << q4.qshift;
+      d = inv1(px, __shfl_sync(FULL, d, rowb), __shfl_sync(FULL, d, rowb + 1), __shfl_sync(FULL, d, rowb + 2), __shfl_sync(FULL, d, rowb + 3));
+      d = inv1(py, __shfl_sync(FULL, d, colb), __shfl_sync(FULL, d, colb + 4), __shfl_sync(FULL, d, colb + 8), __shfl_sync(FULL, d, colb + 12));
+      if (lane < 16) i4.rec[by * 4 + py][bx * 4 + px] = (uint8_t)clip255(pred + ((d + 32) >> 6));
+      if (lane == 0) { i4.modes[by * 4 + bx] = (uint8_t)mode; i4.nnz[by * 4 + bx] = (uint8_t)__popc(nzm); }
+      __syncwarp();
+    }
+    // I4 luma size + distortion
+    int cbp4 = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) if (i4.nnz[blk_y[b] * 4 + blk_x[b]]) cbp4 |= 1 << (b >> 2);
+    int bits4_cavlc;
+    {
+      CountSink cs;
+      if (lane >= 1 && lane <= 16 && ((cbp4 >> ((lane - 1) >> 2)) & 1)) cavlc_block(cs, &i4.lv[lane - 1][0], 16, NC_WORST);
+      bits4_cavlc = __reduce_add_sync(FULL, cs.n);
+    }
+    long long d4;
+    {
+      int s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)i4.rec[r8][c8 + j]; s += e * e; }
+      d4 = __reduce_add_sync(FULL, s);
+    }
+    // ---- Intra16x16 coding (also codes the chroma, which is identical either way) --------------------------
+    int luma_bits16, chroma_bits;
+    int16_t* coef_mb = f.coef + (size_t)mb * COEF_BLOCKS * 16;
+    uint8_t* nnz_mb = f.nnz + (size_t)mb * 32;
+    int cbp = transform_mb<true>(t, lane, qp, coef_mb, nnz_mb, luma_bits16, chroma_bits);
     __syncwarp();
+    long long d16;
+    {
+      int s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)t.rec_y[r8][c8 + j]; s += e * e; }
+      d16 = __reduce_add_sync(FULL, s);
+    }
+    const long long l2 = rd_lambda[qp];
+    const bool use_i4 = d4 + l2 * (8 + bits4_cavlc + mode_bits4) < d16 + l2 * (8 + luma_bits16);
+    int est;
+    if (use_i4) {     // commit the 4x4 result over the 16x16 one
+      *reinterpret_cast<uint2*>(&t.rec_y[r8][c8]) = *reinterpret_cast<const uint2*>(&i4.rec[r8][c8]);
+      if (lane < 16) {
+        const uint4* src = reinterpret_cast<const uint4*>(&i4.lv[lane][0]);
+        uint4* dst = reinterpret_cast<uint4*>(coef_mb + (1 + lane) * 16);
+        dst[0] = src[0]; dst[1] = src[1];
+        nnz_mb[lane] = i4.nnz[lane];
+        f.i4modes[(size_t)mb * 16 + lane] = i4.modes[lane];
+      }
+      cbp = cbp4 | (cbp & 0x30);
+      est = 96 + bits4_cavlc + chroma_bits;
+    } else {
+      est = 48 + luma_bits16 + chroma_bits;
+    }
+    int type = use_i4 ? MB_I4 : MB_I16;
+    __syncwarp();
+    if (est > MB_BITS_LIMIT) { apply_pcm(t, lane, nnz_mb); type = MB_PCM; cbp = 0; __syncwarp(); }   // A.3.1: send raw
     {
       const uint2 v = *reinterpret_cast<const uint2*>(&t.rec_y[r8][c8]);
       *reinterpret_cast<uint2*>(rec_y + (size_t)(mby * 16 + r8) * f.cw + mbx * 16 + c8) = v;
@@ -151,15 +358,19 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       // right column becomes the next macroblock's left neighbour
       if (lane < 16) nb.left_y[lane] = t.rec_y[lane][15];
       else nb.left_uv[lane - 16] = t.rec_uv[(lane - 16) >> 1][14 + ((lane - 16) & 1)];
+      if (lane < 4) nb.left_modes[lane] = type == MB_I4 ? i4.modes[lane * 4 + 3] : (uint8_t)2;
       if (lane == 0) {
-        MbInfo mi; mi.mvx = 0; mi.mvy = 0; mi.type = MB_I16; mi.i16_mode = (uint8_t)best_mode; mi.chroma_mode = (uint8_t)cbest; mi.cbp = (uint8_t)cbp;
-        if (cbp < 0) { mi.type = MB_PCM; mi.cbp = 0; }   // too big for CAVLC: I_PCM (transform_mb)
+        MbInfo mi; mi.mvx = 0; mi.mvy = 0; mi.type = (uint8_t)type; mi.i16_mode = (uint8_t)best_mode; mi.chroma_mode = (uint8_t)cbest; mi.cbp = (uint8_t)cbp;
         f.mbinfo[mb] = mi;
       }
     }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) *((volatile int*)&f.progress[mby]) = mbx + 1;
+    if (signal_progress) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) *((volatile int*)&f.progress[mby]) = mbx + 1;
+    } else {
+      __syncwarp();
+    }
   }
 }
 

@@ -84,6 +84,33 @@ def test_pcm_fallback_bit_exact(qp, slice_rows):
     assert len(dec) == 3 and np.array_equal(dec[2][0], grec[0][:h, :w])
 
 
+def natural_frames(w, h):
+    """Anti-aliased text and a photo-like texture: content where Intra4x4 wins the rate-distortion decision."""
+    cv2 = pytest.importorskip("cv2")
+    img = np.full((h, w, 3), 245, np.uint8)
+    for i, y in enumerate(range(20, h, 20)):
+        cv2.putText(img, "The quick brown fox jumps over the lazy dog 0123456789"[i % 9:], (6, y), cv2.FONT_HERSHEY_SIMPLEX, 0.5, (20, 20, 20), 1, cv2.LINE_AA)
+    cv2.circle(img, (w * 3 // 4, h // 2), h // 5, (200, 80, 40), -1, cv2.LINE_AA)
+    text = np.dstack([img, np.full((h, w), 255, np.uint8)])
+    rng = np.random.default_rng(3)
+    a = cv2.GaussianBlur(rng.normal(0, 1, (h, w, 3)).astype(np.float32), (0, 0), 5) * 800 + \
+        cv2.GaussianBlur(rng.normal(0, 1, (h, w, 3)).astype(np.float32), (0, 0), 1.2) * 40 + 128
+    photo = np.dstack([np.clip(a, 0, 255).astype(np.uint8), np.full((h, w), 255, np.uint8)])
+    return [text, photo]
+
+
+@pytest.mark.parametrize("slice_rows", [1, 3, 100])
+@pytest.mark.parametrize("qp", [20, 34])
+def test_intra4x4_bit_exact(slice_rows, qp):
+    """Intra4x4 (9 modes, above-right availability across macroblock and slice boundaries) + the I4/I16 RD decision."""
+    w, h = 320, 192
+    frames = natural_frames(w, h) + [synth.gradient(w, h, 1)]
+    got, ref, grec, rrec = encode_both(w, h, frames, qp=qp, slice_rows=slice_rows, idr_at=(0, 1, 2))
+    assert_same(got, ref, grec, rrec)
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert np.array_equal(dec[2][0], grec[0][:h, :w])
+
+
 def test_static_scene_is_skipped():
     f = synth.desktop(320, 192, 0)
     got, ref, grec, rrec = encode_both(320, 192, [f, f, f], qp=30)
