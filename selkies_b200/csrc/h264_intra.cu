@@ -35,50 +35,30 @@ struct I4State {
   int16_t lv[16][16];                        // [blkIdx][scan position]
   uint8_t nnz[16];                           // raster block position
   uint8_t modes[16];                         // raster block position
-  uint8_t ed[16];                            // edge samples of the current block: l3 l2 l1 l0 | M | t0..t7
+  uint8_t v[64];                             // X | F2 | F3 | DC of the current block (see i4_pred_code)
+  uint8_t code[9][16];                       // shared-memory copy of i4_pred_code
 };
 
 __device__ __forceinline__ int f3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
 __device__ __forceinline__ int f2(int a, int b) { return (a + b + 1) >> 1; }
 
-// 8.3.1.2.1-9; e[0..3] = left samples bottom..top, e[4] = top-left, e[5..12] = top + top-right
-__device__ __forceinline__ int pred4_pixel(int mode, int x, int y, const uint8_t* e, bool has_a, bool has_b) {
-  const uint8_t* t = e + 5;
-#define L4(i) ((i) < 0 ? (int)e[4] : (int)e[3 - (i)])
-  switch (mode) {
-    case 0: return t[x];
-    case 1: return L4(y);
-    case 2: {
-      const int st = t[0] + t[1] + t[2] + t[3], sl = e[0] + e[1] + e[2] + e[3];
-      return has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128;
-    }
-    case 3: return (x == 3 && y == 3) ? (t[6] + 3 * t[7] + 2) >> 2 : f3(t[x + y], t[x + y + 1], t[x + y + 2]);
-    case 4: return f3(e[4 + x - y - 1], e[4 + x - y], e[4 + x - y + 1]);
-    case 5: {
-      const int z = 2 * x - y;
-      if (z >= 0 && !(z & 1)) return f2(t[x - (y >> 1) - 1], t[x - (y >> 1)]);
-      if (z >= 0) return f3(t[x - (y >> 1) - 2], t[x - (y >> 1) - 1], t[x - (y >> 1)]);
-      if (z == -1) return f3(L4(0), e[4], t[0]);
-      return f3(L4(y - 1), L4(y - 2), L4(y - 3));
-    }
-    case 6: {
-      const int z = 2 * y - x;
-      if (z >= 0 && !(z & 1)) return f2(L4(y - (x >> 1) - 1), L4(y - (x >> 1)));
-      if (z >= 0) return f3(L4(y - (x >> 1) - 2), L4(y - (x >> 1) - 1), L4(y - (x >> 1)));
-      if (z == -1) return f3(L4(0), e[4], t[0]);
-      return f3(t[x - 1], t[x - 2], t[x - 3]);
-    }
-    case 7: return (y & 1) ? f3(t[x + (y >> 1)], t[x + (y >> 1) + 1], t[x + (y >> 1) + 2]) : f2(t[x + (y >> 1)], t[x + (y >> 1) + 1]);
-    default: {
-      const int z = x + 2 * y;
-      if (z > 5) return L4(3);
-      if (z == 5) return (L4(2) + 3 * L4(3) + 2) >> 2;
-      if (z & 1) return f3(L4(y + (x >> 1)), L4(y + (x >> 1) + 1), L4(y + (x >> 1) + 2));
-      return f2(L4(y + (x >> 1)), L4(y + (x >> 1) + 1));
-    }
-  }
-#undef L4
-}
+// Intra4x4 prediction as a table lookup (8.3.1.2.1-9).  The 13 neighbouring samples are laid out as
+//   X[0] = l3 (dup), X[1..4] = l3 l2 l1 l0, X[5] = M (above-left), X[6..13] = t0..t7, X[14] = t7 (dup)
+// and every predicted sample of every mode is one of: X[i] (code i), F2[i] = (X[i]+X[i+1]+1)>>1 (code 16+i),
+// F3[i] = (X[i-1]+2X[i]+X[i+1]+2)>>2 (code 32+i) or the DC value (code 48).  One shared-memory array V[64] holds all
+// of them, so the nine modes are evaluated without any divergent control flow.  (Generated from the formulas of the
+// Recommendation and checked against them exhaustively; the CPU oracle evaluates the formulas directly.)
+__device__ const uint8_t i4_pred_code[9][16] = {
+  { 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9 },                     // 0 vertical
+  { 4, 4, 4, 4, 3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1 },                     // 1 horizontal
+  { 48, 48, 48, 48, 48, 48, 48, 48, 48, 48, 48, 48, 48, 48, 48, 48 },     // 2 DC
+  { 39, 40, 41, 42, 40, 41, 42, 43, 41, 42, 43, 44, 42, 43, 44, 45 },     // 3 diagonal down-left
+  { 37, 38, 39, 40, 36, 37, 38, 39, 35, 36, 37, 38, 34, 35, 36, 37 },     // 4 diagonal down-right
+  { 21, 22, 23, 24, 37, 38, 39, 40, 36, 21, 22, 23, 35, 37, 38, 39 },     // 5 vertical-right
+  { 20, 37, 38, 39, 19, 36, 20, 37, 18, 35, 19, 36, 17, 34, 18, 35 },     // 6 horizontal-down
+  { 22, 23, 24, 25, 39, 40, 41, 42, 23, 24, 25, 26, 40, 41, 42, 43 },     // 7 vertical-left
+  { 19, 35, 18, 34, 18, 34, 17, 33, 17, 33, 1, 1, 1, 1, 1, 1 },           // 8 horizontal-up
+};
 __device__ __forceinline__ bool i4_mode_ok(int mode, bool has_a, bool has_b, bool has_d) {
   switch (mode) {
     case 0: case 3: case 7: return has_b;
@@ -116,6 +96,7 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
   const int rc4 = lane >> 2, cc4 = (lane & 3) * 4;          // this lane's 4 interleaved chroma bytes
   const QuantParams q4 = make_quant(qp, true);
   if (lane < 4) nb.left_modes[lane] = 2;
+  for (int i = lane; i < 144; i += 32) (&i4.code[0][0])[i] = (&i4_pred_code[0][0])[i];
 
   for (int mbx = 0; mbx < f.mbw; mbx++) {
     const int mb = mby * f.mbw + mbx;
@@ -241,18 +222,26 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       const bool has_d = (bx > 0 && by > 0) ? true : bx > 0 ? has_top : by > 0 ? has_left : (has_left && has_top);
       const int trc = i4_tr_inside[by * 4 + bx];
       const bool has_c = trc == 1 ? true : trc == 2 ? has_top : trc == 3 ? has_tr : false;
-      if (lane < 13) {        // edge samples of this block
+      if (lane < 15) {        // X[lane]: neighbouring samples of this block (128 where unavailable: never selected)
         int v = 128;
-        if (lane < 4) {
-          const int k = 3 - lane;
+        if (lane < 5) {
+          const int k = lane == 0 ? 3 : 4 - lane;
           if (has_a) v = bx > 0 ? i4.rec[by * 4 + k][bx * 4 - 1] : nb.left_y[by * 4 + k];
-        } else if (lane == 4) {
+        } else if (lane == 5) {
           if (has_d) v = (bx > 0 && by > 0) ? (int)i4.rec[by * 4 - 1][bx * 4 - 1] : bx > 0 ? (int)nb.top_y[bx * 4 - 1] : by > 0 ? (int)nb.left_y[by * 4 - 1] : nb.tl_y;
         } else if (has_b) {
-          const int j = (lane - 5 < 4 || has_c) ? lane - 5 : 3;        // 8.3.1.2: missing above-right samples repeat p[3,-1]
+          int j = lane == 14 ? 7 : lane - 6;
+          if (j >= 4 && !has_c) j = 3;                                  // 8.3.1.2: missing above-right samples repeat p[3,-1]
           v = by > 0 ? i4.rec[by * 4 - 1][bx * 4 + j] : nb.top_y[bx * 4 + j];
         }
-        i4.ed[lane] = (uint8_t)v;
+        i4.v[lane] = (uint8_t)v;
+      }
+      __syncwarp();
+      if (lane < 14) i4.v[16 + lane] = (uint8_t)f2(i4.v[lane], i4.v[lane + 1]);
+      else if (lane >= 16 && lane < 29) { const int i = lane - 15; i4.v[32 + i] = (uint8_t)f3(i4.v[i - 1], i4.v[i], i4.v[i + 1]); }
+      else if (lane == 31) {
+        const int st = i4.v[6] + i4.v[7] + i4.v[8] + i4.v[9], sl = i4.v[1] + i4.v[2] + i4.v[3] + i4.v[4];
+        i4.v[48] = (uint8_t)(has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128);
       }
       __syncwarp();
       // predicted mode (8.3.1.1)
@@ -265,13 +254,11 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       // modes 0..7: lane = mode*4 + row; mode 8: every group of four lanes evaluates it as well
       const int m = lane >> 2, y = lane & 3;
       const uint32_t crow = *reinterpret_cast<const uint32_t*>(&t.cur_y[by * 4 + y][bx * 4]);
-      int sad_m = 0, sad_hu = 0;
-#pragma unroll
-      for (int x = 0; x < 4; x++) {
-        const int c = (crow >> (8 * x)) & 255;
-        sad_m += abs(c - pred4_pixel(m, x, y, i4.ed, has_a, has_b));
-        sad_hu += abs(c - pred4_pixel(8, x, y, i4.ed, has_a, has_b));
-      }
+      const uint32_t cm = *reinterpret_cast<const uint32_t*>(&i4.code[m][y * 4]);
+      const uint32_t ch = *reinterpret_cast<const uint32_t*>(&i4.code[8][y * 4]);
+      const uint32_t pm4 = (uint32_t)i4.v[cm & 255] | ((uint32_t)i4.v[(cm >> 8) & 255] << 8) | ((uint32_t)i4.v[(cm >> 16) & 255] << 16) | ((uint32_t)i4.v[cm >> 24] << 24);
+      const uint32_t p84 = (uint32_t)i4.v[ch & 255] | ((uint32_t)i4.v[(ch >> 8) & 255] << 8) | ((uint32_t)i4.v[(ch >> 16) & 255] << 16) | ((uint32_t)i4.v[ch >> 24] << 24);
+      int sad_m = (int)__vsadu4(crow, pm4), sad_hu = (int)__vsadu4(crow, p84);
       sad_m += __shfl_xor_sync(FULL, sad_m, 1); sad_m += __shfl_xor_sync(FULL, sad_m, 2);
       sad_hu += __shfl_xor_sync(FULL, sad_hu, 1); sad_hu += __shfl_xor_sync(FULL, sad_hu, 2);
       uint32_t key = 0xffffffffu;
@@ -282,7 +269,7 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       mode_bits4 += mode == pm ? 1 : 4;
       // lanes 0..15: one sample each; transform / quantise / reconstruct with shuffles (lanes 16..31 mirror 0..15)
       const int px = lane & 3, py = (lane >> 2) & 3, rpos = py * 4 + px;
-      const int pred = pred4_pixel(mode, px, py, i4.ed, has_a, has_b);
+      const int pred = i4.v[i4.code[mode][rpos]];
       const int res = (int)t.cur_y[by * 4 + py][bx * 4 + px] - pred;
       const int rowb = lane & ~3, colb = (lane & 16) | px;
       int v = fwd1(px, __shfl_sync(FULL, res, rowb), __shfl_sync(FULL, res, rowb + 1), __shfl_sync(FULL, res, rowb + 2), __shfl_sync(FULL, res, rowb + 3));
