@@ -346,6 +346,7 @@ static void pred8c(int mode, const uint8_t* top, const uint8_t* left, int tl, in
 static int sad_n(const uint8_t* a, const uint8_t* b, int n) { int s = 0; for (int i = 0; i < n; i++) s += iabs(a[i] - b[i]); return s; }
 
 
+#define I4_SKIP_SAD_PER_LAMBDA 32   /* Intra4x4 is only tried when the best Intra16x16 SAD exceeds 32*lambda */
 /* ------------------------------------------------------------------ Intra4x4 (8.3.1) */
 /* e[0..3] = left samples bottom..top (l3,l2,l1,l0), e[4] = top-left M, e[5..12] = top samples t0..t7 (t4..t7 = top-right) */
 static int f3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
@@ -483,6 +484,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     int key = sad_n(cy, pred, 256) * 4 + mode;
     if (key < best_key) { best_key = key; m->i16_mode = (int8_t)mode; memcpy(best_pred, pred, 256); }
   }
+  const int try_i4 = (best_key >> 2) > I4_SKIP_SAD_PER_LAMBDA * me_lambda[qp];   /* nearly flat: straight to Intra16x16 */
   uint8_t cpred[2][64], best_cpred[2][64]; best_key = 1 << 30;
   for (int mode = 0; mode < 4; mode++) {
     if ((mode == 2 && !has_top) || (mode == 1 && !has_left) || (mode == 3 && !(has_top && has_left))) continue;
@@ -493,7 +495,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   /* Intra4x4 candidate: run completely first (it needs its own reconstruction block by block) and saved; the
    * Intra16x16 coding below then overwrites frame and macroblock state, and the rate-distortion comparison at the
    * end restores the 4x4 result if it wins. */
-  intra4x4_pass(e, m, cy, mbx, mby, qp);
+  if (try_i4) intra4x4_pass(e, m, cy, mbx, mby, qp);
   mb_t m4 = *m;
   uint8_t rec4[256];
   for (int r = 0; r < 16; r++) memcpy(rec4 + 16 * r, ry + (size_t)(mby * 16 + r) * e->cw + mbx * 16, 16);
@@ -530,7 +532,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     }
   }
   /* mode decision J = SSD + lambda_rd * bits over the luma (chroma is coded identically either way) */
-  {
+  if (try_i4) {
     int64_t d16 = 0, d4 = 0;
     for (int r = 0; r < 16; r++)
       for (int c = 0; c < 16; c++) {

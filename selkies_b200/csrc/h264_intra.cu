@@ -18,6 +18,8 @@
 
 namespace b2v {
 
+constexpr int I4_SKIP_SAD_PER_LAMBDA = 32;   // Intra4x4 is only tried when the best Intra16x16 SAD exceeds 32*lambda
+
 __device__ __forceinline__ uint32_t rep4(int v) { return (uint32_t)v * 0x01010101u; }
 
 struct IntraNb {
@@ -31,7 +33,7 @@ struct IntraNb {
 };
 
 struct I4State {
-  uint8_t rec[16][16];
+  uint8_t rt[17][24];                        // framed reconstruction (see the Intra4x4 pass)
   int16_t lv[16][16];                        // [blkIdx][scan position]
   uint8_t nnz[16];                           // raster block position
   uint8_t modes[16];                         // raster block position
@@ -67,9 +69,8 @@ __device__ __forceinline__ bool i4_mode_ok(int mode, bool has_a, bool has_b, boo
     default: return has_a && has_b && has_d;
   }
 }
-// above-right availability of block (bx,by) inside the macroblock, raster: 1 inside, 2 from the MB above, 3 above-right MB
-__device__ const uint8_t i4_tr_inside[16] = { 2,2,2,3, 1,0,1,0, 1,1,1,0, 1,0,1,0 };
-__device__ const uint8_t inv_zigzag4x4[16] = { 0,1,5,6, 2,4,7,12, 3,8,11,13, 9,10,14,15 };   // raster -> scan position
+// (above-right availability inside the macroblock and the inverse zig-zag are nibble-packed literals in the kernel:
+//  raster { 2,2,2,3, 1,0,1,0, 1,1,1,0, 1,0,1,0 } with 1 = inside, 2 = macroblock above, 3 = above-right macroblock)
 
 // one 1-D stage of the forward / inverse core transform for the element `k` of (a,b,c,d)
 __device__ __forceinline__ int fwd1(int k, int a, int b, int c, int d) {
@@ -95,8 +96,17 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
   const int r8 = lane >> 1, c8 = (lane & 1) * 8;            // this lane's 8 luma pixels
   const int rc4 = lane >> 2, cc4 = (lane & 3) * 4;          // this lane's 4 interleaved chroma bytes
   const QuantParams q4 = make_quant(qp, true);
+  // lane-invariant roles inside the Intra4x4 pass
+  const int px = lane & 3, py = (lane >> 2) & 3, rpos = py * 4 + px, rowb = lane & ~3, colb = (lane & 16) | px;
+  const int cls = pos_class(rpos), mf_l = q4.mf[cls], dq_l = q4.dq[cls];
+  const int izz = (int)((0xFEA9DB83C7426510ull >> (4 * rpos)) & 15ull);      // raster -> scan position (inverse zig-zag), nibble-packed
+  const int lm = lane >> 2, ly = lane & 3;                                    // candidate mode / row evaluated by this lane
+  const int lm_need = (lm == 0 || lm == 3 || lm == 7) ? 0 : lm == 1 ? 1 : lm == 2 ? 2 : 3;   // needs: above / left / nothing / all three
   if (lane < 4) nb.left_modes[lane] = 2;
   for (int i = lane; i < 144; i += 32) (&i4.code[0][0])[i] = (&i4_pred_code[0][0])[i];
+  __syncwarp();
+  const uint32_t cm = *reinterpret_cast<const uint32_t*>(&i4.code[lm][ly * 4]);   // V-indices of this lane's four predicted samples
+  const uint32_t ch = *reinterpret_cast<const uint32_t*>(&i4.code[8][ly * 4]);    // ... for horizontal-up
 
   for (int mbx = 0; mbx < f.mbw; mbx++) {
     const int mb = mby * f.mbw + mbx;
@@ -215,92 +225,86 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
     __syncwarp();
 
     // ---- Intra4x4 candidate: 16 blocks in decoding order ----------------------------------------------
-    int mode_bits4 = 0;
-    for (int blk = 0; blk < 16; blk++) {
-      const int bx = blk_x[blk], by = blk_y[blk];
-      const bool has_a = bx > 0 || has_left, has_b = by > 0 || has_top;
-      const bool has_d = (bx > 0 && by > 0) ? true : bx > 0 ? has_top : by > 0 ? has_left : (has_left && has_top);
-      const int trc = i4_tr_inside[by * 4 + bx];
-      const bool has_c = trc == 1 ? true : trc == 2 ? has_top : trc == 3 ? has_tr : false;
-      if (lane < 15) {        // X[lane]: neighbouring samples of this block (128 where unavailable: never selected)
-        int v = 128;
-        if (lane < 5) {
-          const int k = lane == 0 ? 3 : 4 - lane;
-          if (has_a) v = bx > 0 ? i4.rec[by * 4 + k][bx * 4 - 1] : nb.left_y[by * 4 + k];
-        } else if (lane == 5) {
-          if (has_d) v = (bx > 0 && by > 0) ? (int)i4.rec[by * 4 - 1][bx * 4 - 1] : bx > 0 ? (int)nb.top_y[bx * 4 - 1] : by > 0 ? (int)nb.left_y[by * 4 - 1] : nb.tl_y;
-        } else if (has_b) {
-          int j = lane == 14 ? 7 : lane - 6;
-          if (j >= 4 && !has_c) j = 3;                                  // 8.3.1.2: missing above-right samples repeat p[3,-1]
-          v = by > 0 ? i4.rec[by * 4 - 1][bx * 4 + j] : nb.top_y[bx * 4 + j];
+    // rt = reconstruction with a one-sample frame: rt[y+1][x+1] is macroblock sample (x,y), row 0 / column 0 hold the
+    // neighbours above (16 + 4 above-right) and to the left, rt[0][0] the above-left sample.
+    const bool try_i4 = (best_key >> 2) > I4_SKIP_SAD_PER_LAMBDA * lambda;      // nearly flat macroblocks go straight to Intra16x16
+    int mode_bits4 = 0, cbp4 = 0, bits4_cavlc = 0;
+    long long d4 = 0;
+    if (try_i4) {
+      if (lane < 20) i4.rt[0][1 + lane] = nb.top_y[lane];
+      if (lane < 16) i4.rt[1 + lane][0] = nb.left_y[lane];
+      if (lane == 31) i4.rt[0][0] = (uint8_t)nb.tl_y;
+      __syncwarp();
+      for (int blk = 0; blk < 16; blk++) {
+        const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
+        const bool has_a = bx > 0 || has_left, has_b = by > 0 || has_top;
+        const bool has_d = (bx > 0 && by > 0) ? true : bx > 0 ? has_top : by > 0 ? has_left : (has_left && has_top);
+        const int trc = (int)((0x111511eau >> (2 * (by * 4 + bx))) & 3u);      // 2-bit codes of i4_tr_inside, raster order
+        const bool has_c = trc == 1 ? true : trc == 2 ? has_top : trc == 3 ? has_tr : false;
+        if (lane < 15) {        // X[lane]: neighbouring samples of this block (values of unavailable ones are never selected)
+          int row = by * 4, col = bx * 4;
+          if (lane < 5) row += (lane == 0 ? 3 : 4 - lane) + 1;
+          else if (lane > 5) { int j = lane == 14 ? 7 : lane - 6; if (j >= 4 && !has_c) j = 3; col += 1 + j; }   // 8.3.1.2: repeat p[3,-1]
+          i4.v[lane] = i4.rt[row][col];
         }
-        i4.v[lane] = (uint8_t)v;
+        __syncwarp();
+        if (lane < 14) i4.v[16 + lane] = (uint8_t)f2(i4.v[lane], i4.v[lane + 1]);
+        else if (lane >= 16 && lane < 29) { const int i = lane - 15; i4.v[32 + i] = (uint8_t)f3(i4.v[i - 1], i4.v[i], i4.v[i + 1]); }
+        else if (lane == 31) {
+          const int st = i4.v[6] + i4.v[7] + i4.v[8] + i4.v[9], sl = i4.v[1] + i4.v[2] + i4.v[3] + i4.v[4];
+          i4.v[48] = (uint8_t)(has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128);
+        }
+        __syncwarp();
+        // predicted mode (8.3.1.1)
+        int pm;
+        {
+          const int ma = bx > 0 ? (int)i4.modes[by * 4 + bx - 1] : has_left ? (int)nb.left_modes[by] : -1;
+          const int mb_ = by > 0 ? (int)i4.modes[(by - 1) * 4 + bx] : has_top ? (int)nb.top_modes[bx] : -1;
+          pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
+        }
+        // modes 0..7: lane = mode*4 + row; mode 8: every group of four lanes evaluates it as well
+        const uint32_t crow = *reinterpret_cast<const uint32_t*>(&t.cur_y[by * 4 + ly][bx * 4]);
+        const uint32_t pm4 = (uint32_t)i4.v[cm & 255] | ((uint32_t)i4.v[(cm >> 8) & 255] << 8) | ((uint32_t)i4.v[(cm >> 16) & 255] << 16) | ((uint32_t)i4.v[cm >> 24] << 24);
+        const uint32_t p84 = (uint32_t)i4.v[ch & 255] | ((uint32_t)i4.v[(ch >> 8) & 255] << 8) | ((uint32_t)i4.v[(ch >> 16) & 255] << 16) | ((uint32_t)i4.v[ch >> 24] << 24);
+        int sad_m = (int)__vsadu4(crow, pm4), sad_hu = (int)__vsadu4(crow, p84);
+        sad_m += __shfl_xor_sync(FULL, sad_m, 1); sad_hu += __shfl_xor_sync(FULL, sad_hu, 1);
+        sad_m += __shfl_xor_sync(FULL, sad_m, 2); sad_hu += __shfl_xor_sync(FULL, sad_hu, 2);
+        const bool ok_m = lm_need == 0 ? has_b : lm_need == 1 ? has_a : lm_need == 2 ? true : (has_a && has_b && has_d);
+        uint32_t key = 0xffffffffu;
+        if (ok_m) key = (uint32_t)((sad_m + lambda * (lm == pm ? 1 : 4)) * 16 + lm);
+        if (has_a) key = min(key, (uint32_t)((sad_hu + lambda * (8 == pm ? 1 : 4)) * 16 + 8));
+        key = __reduce_min_sync(FULL, key);
+        const int mode = key & 15;
+        mode_bits4 += mode == pm ? 1 : 4;
+        // lanes 0..15: one sample each; transform / quantise / reconstruct with shuffles (lanes 16..31 mirror 0..15)
+        const int pred = i4.v[i4.code[mode][rpos]];
+        const int res = (int)t.cur_y[by * 4 + py][bx * 4 + px] - pred;
+        int v = fwd1(px, __shfl_sync(FULL, res, rowb), __shfl_sync(FULL, res, rowb + 1), __shfl_sync(FULL, res, rowb + 2), __shfl_sync(FULL, res, rowb + 3));
+        v = fwd1(py, __shfl_sync(FULL, v, colb), __shfl_sync(FULL, v, colb + 4), __shfl_sync(FULL, v, colb + 8), __shfl_sync(FULL, v, colb + 12));
+        const int level = quant1(v, mf_l, q4.f, q4.qbits);
+        const unsigned nzm = __ballot_sync(FULL, level != 0) & 0xffffu;
+        if (lane < 16) i4.lv[blk][izz] = (int16_t)level;
+        int d = (level * dq_l) << q4.qshift;
+        d = inv1(px, __shfl_sync(FULL, d, rowb), __shfl_sync(FULL, d, rowb + 1), __shfl_sync(FULL, d, rowb + 2), __shfl_sync(FULL, d, rowb + 3));
+        d = inv1(py, __shfl_sync(FULL, d, colb), __shfl_sync(FULL, d, colb + 4), __shfl_sync(FULL, d, colb + 8), __shfl_sync(FULL, d, colb + 12));
+        if (lane < 16) i4.rt[by * 4 + py + 1][bx * 4 + px + 1] = (uint8_t)clip255(pred + ((d + 32) >> 6));
+        if (lane == 0) { i4.modes[by * 4 + bx] = (uint8_t)mode; i4.nnz[by * 4 + bx] = (uint8_t)__popc(nzm); }
+        __syncwarp();
       }
-      __syncwarp();
-      if (lane < 14) i4.v[16 + lane] = (uint8_t)f2(i4.v[lane], i4.v[lane + 1]);
-      else if (lane >= 16 && lane < 29) { const int i = lane - 15; i4.v[32 + i] = (uint8_t)f3(i4.v[i - 1], i4.v[i], i4.v[i + 1]); }
-      else if (lane == 31) {
-        const int st = i4.v[6] + i4.v[7] + i4.v[8] + i4.v[9], sl = i4.v[1] + i4.v[2] + i4.v[3] + i4.v[4];
-        i4.v[48] = (uint8_t)(has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128);
-      }
-      __syncwarp();
-      // predicted mode (8.3.1.1)
-      int pm;
+      // I4 luma size + distortion
+#pragma unroll
+      for (int b = 0; b < 16; b++) if (i4.nnz[(((b >> 3) * 2 + ((b >> 1) & 1)) * 4) + ((b >> 2) & 1) * 2 + (b & 1)]) cbp4 |= 1 << (b >> 2);
       {
-        const int ma = bx > 0 ? (int)i4.modes[by * 4 + bx - 1] : has_left ? (int)nb.left_modes[by] : -1;
-        const int mb_ = by > 0 ? (int)i4.modes[(by - 1) * 4 + bx] : has_top ? (int)nb.top_modes[bx] : -1;
-        pm = (ma < 0 || mb_ < 0) ? 2 : min(ma, mb_);
+        CountSink cs;
+        if (lane >= 1 && lane <= 16 && ((cbp4 >> ((lane - 1) >> 2)) & 1)) cavlc_block(cs, &i4.lv[lane - 1][0], 16, NC_WORST);
+        bits4_cavlc = __reduce_add_sync(FULL, cs.n);
       }
-      // modes 0..7: lane = mode*4 + row; mode 8: every group of four lanes evaluates it as well
-      const int m = lane >> 2, y = lane & 3;
-      const uint32_t crow = *reinterpret_cast<const uint32_t*>(&t.cur_y[by * 4 + y][bx * 4]);
-      const uint32_t cm = *reinterpret_cast<const uint32_t*>(&i4.code[m][y * 4]);
-      const uint32_t ch = *reinterpret_cast<const uint32_t*>(&i4.code[8][y * 4]);
-      const uint32_t pm4 = (uint32_t)i4.v[cm & 255] | ((uint32_t)i4.v[(cm >> 8) & 255] << 8) | ((uint32_t)i4.v[(cm >> 16) & 255] << 16) | ((uint32_t)i4.v[cm >> 24] << 24);
-      const uint32_t p84 = (uint32_t)i4.v[ch & 255] | ((uint32_t)i4.v[(ch >> 8) & 255] << 8) | ((uint32_t)i4.v[(ch >> 16) & 255] << 16) | ((uint32_t)i4.v[ch >> 24] << 24);
-      int sad_m = (int)__vsadu4(crow, pm4), sad_hu = (int)__vsadu4(crow, p84);
-      sad_m += __shfl_xor_sync(FULL, sad_m, 1); sad_m += __shfl_xor_sync(FULL, sad_m, 2);
-      sad_hu += __shfl_xor_sync(FULL, sad_hu, 1); sad_hu += __shfl_xor_sync(FULL, sad_hu, 2);
-      uint32_t key = 0xffffffffu;
-      if (i4_mode_ok(m, has_a, has_b, has_d)) key = (uint32_t)((sad_m + lambda * (m == pm ? 1 : 4)) * 16 + m);
-      if (has_a) key = min(key, (uint32_t)((sad_hu + lambda * (8 == pm ? 1 : 4)) * 16 + 8));
-      key = __reduce_min_sync(FULL, key);
-      const int mode = key & 15;
-      mode_bits4 += mode == pm ? 1 : 4;
-      // lanes 0..15: one sample each; transform / quantise / reconstruct with shuffles (lanes 16..31 mirror 0..15)
-      const int px = lane & 3, py = (lane >> 2) & 3, rpos = py * 4 + px;
-      const int pred = i4.v[i4.code[mode][rpos]];
-      const int res = (int)t.cur_y[by * 4 + py][bx * 4 + px] - pred;
-      const int rowb = lane & ~3, colb = (lane & 16) | px;
-      int v = fwd1(px, __shfl_sync(FULL, res, rowb), __shfl_sync(FULL, res, rowb + 1), __shfl_sync(FULL, res, rowb + 2), __shfl_sync(FULL, res, rowb + 3));
-      v = fwd1(py, __shfl_sync(FULL, v, colb), __shfl_sync(FULL, v, colb + 4), __shfl_sync(FULL, v, colb + 8), __shfl_sync(FULL, v, colb + 12));
-      const int cls = pos_class(rpos);
-      const int level = quant1(v, q4.mf[cls], q4.f, q4.qbits);
-      const unsigned nzm = __ballot_sync(FULL, level != 0) & 0xffffu;
-      if (lane < 16) i4.lv[blk][inv_zigzag4x4[rpos]] = (int16_t)level;
-      int d = (level * q4.dq[cls]) << q4.qshift;
-      d = inv1(px, __shfl_sync(FULL, d, rowb), __shfl_sync(FULL, d, rowb + 1), __shfl_sync(FULL, d, rowb + 2), __shfl_sync(FULL, d, rowb + 3));
-      d = inv1(py, __shfl_sync(FULL, d, colb), __shfl_sync(FULL, d, colb + 4), __shfl_sync(FULL, d, colb + 8), __shfl_sync(FULL, d, colb + 12));
-      if (lane < 16) i4.rec[by * 4 + py][bx * 4 + px] = (uint8_t)clip255(pred + ((d + 32) >> 6));
-      if (lane == 0) { i4.modes[by * 4 + bx] = (uint8_t)mode; i4.nnz[by * 4 + bx] = (uint8_t)__popc(nzm); }
-      __syncwarp();
-    }
-    // I4 luma size + distortion
-    int cbp4 = 0;
+      {
+        int sd = 0;
 #pragma unroll
-    for (int b = 0; b < 16; b++) if (i4.nnz[blk_y[b] * 4 + blk_x[b]]) cbp4 |= 1 << (b >> 2);
-    int bits4_cavlc;
-    {
-      CountSink cs;
-      if (lane >= 1 && lane <= 16 && ((cbp4 >> ((lane - 1) >> 2)) & 1)) cavlc_block(cs, &i4.lv[lane - 1][0], 16, NC_WORST);
-      bits4_cavlc = __reduce_add_sync(FULL, cs.n);
-    }
-    long long d4;
-    {
-      int s = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)i4.rec[r8][c8 + j]; s += e * e; }
-      d4 = __reduce_add_sync(FULL, s);
+        for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)i4.rt[r8 + 1][c8 + j + 1]; sd += e * e; }
+        d4 = __reduce_add_sync(FULL, sd);
+      }
     }
     // ---- Intra16x16 coding (also codes the chroma, which is identical either way) --------------------------
     int luma_bits16, chroma_bits;
@@ -316,10 +320,11 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       d16 = __reduce_add_sync(FULL, s);
     }
     const long long l2 = rd_lambda[qp];
-    const bool use_i4 = d4 + l2 * (8 + bits4_cavlc + mode_bits4) < d16 + l2 * (8 + luma_bits16);
+    const bool use_i4 = try_i4 && d4 + l2 * (8 + bits4_cavlc + mode_bits4) < d16 + l2 * (8 + luma_bits16);
     int est;
     if (use_i4) {     // commit the 4x4 result over the 16x16 one
-      *reinterpret_cast<uint2*>(&t.rec_y[r8][c8]) = *reinterpret_cast<const uint2*>(&i4.rec[r8][c8]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) t.rec_y[r8][c8 + j] = i4.rt[r8 + 1][c8 + j + 1];
       if (lane < 16) {
         const uint4* src = reinterpret_cast<const uint4*>(&i4.lv[lane][0]);
         uint4* dst = reinterpret_cast<uint4*>(coef_mb + (1 + lane) * 16);
