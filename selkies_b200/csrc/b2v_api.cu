@@ -96,6 +96,7 @@ struct Session {
   std::deque<Job> jobs;
   int64_t submitted = 0, delivered = 0;
   bool stopping = false;
+  bool failed = false; char fail_msg[256] = "";
   std::thread out_thread;
   b2v_stats stats{};
 };
@@ -178,10 +179,19 @@ void output_loop(Session* s) {
     int size = 0, qp = 0;
     const uint8_t* data = nullptr;
     if (s->encode) {
-      cudaEventSynchronize(s->ev_out[j.out_idx]);
+      const cudaError_t se = cudaEventSynchronize(s->ev_out[j.out_idx]);
       uint8_t* base = s->h_out[j.out_idx];
       const AuHeader* ah = (const AuHeader*)base;     // device wrote the AU header at the start of the buffer
       size = ah->size; qp = ah->qp;
+      if (se != cudaSuccess || size < 0 || (size_t)size + sizeof(AuHeader) > s->au_cap || ah->overflow) {
+        // a kernel faulted or produced an impossible access unit: fail loudly — nothing is delivered, every later
+        // call on this session returns B2V_ECUDA with this message
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->failed) snprintf(s->fail_msg, sizeof s->fail_msg, "encode pipeline failed on frame %d: %s (size %d, overflow %d)", j.frame_id,
+                                 se != cudaSuccess ? cudaGetErrorString(se) : "invalid access unit", size, ah->overflow);
+        s->failed = true;
+        size = 0;
+      }
       if ((size_t)size + sizeof(AuHeader) > kFirstChunk && size > 0) {   // oversized AU: fetch the tail
         size_t have = kFirstChunk;
         cudaMemcpyAsync(base + have, s->d_au[j.out_idx] + have, sizeof(AuHeader) + (size_t)size - have, cudaMemcpyDeviceToHost, s->st_out);
@@ -223,7 +233,7 @@ void output_loop(Session* s) {
       }
       s->stats.ms_total_gpu += ms[5];
     }
-    if (s->cb && s->encode) {
+    if (s->cb && s->encode && size > 0) {
       b2v_frame f{};
       f.data = data; f.size = size; f.frame_id = j.frame_id; f.is_key = j.is_key; f.qp = qp;
       f.pts90k = j.pts; f.capture_ns = j.capture_ns;
@@ -250,6 +260,7 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
   EncodeFrameParams fp{};
   {
     std::unique_lock<std::mutex> lk(s->mu);
+    if (s->failed) return fail(B2V_ECUDA, "%s", s->fail_msg);
     out_idx = s->out_next;
     s->cv_slot.wait(lk, [&] { return s->out_free[out_idx] || s->stopping; });
     if (s->stopping) return fail(B2V_ESTATE, "session is stopping");
@@ -437,6 +448,7 @@ int b2v_flush(void* h) {
   if (!s) return fail(B2V_EINVAL, "null handle");
   std::unique_lock<std::mutex> lk(s->mu);
   s->cv_done.wait(lk, [&] { return s->delivered >= s->submitted; });
+  if (s->failed) return fail(B2V_ECUDA, "%s", s->fail_msg);
   return 0;
 }
 

@@ -33,12 +33,12 @@ struct IntraNb {
 };
 
 struct I4State {
+  alignas(16) int16_t lv[16][16];            // [blkIdx][scan position]; read back with 16-byte loads
+  alignas(16) uint8_t code[9][16];           // shared-memory copy of i4_pred_code (read as 32-bit words)
+  alignas(16) uint8_t v[64];                 // X | F2 | F3 | DC of the current block (see i4_pred_code)
   uint8_t rt[17][24];                        // framed reconstruction (see the Intra4x4 pass)
-  int16_t lv[16][16];                        // [blkIdx][scan position]
   uint8_t nnz[16];                           // raster block position
   uint8_t modes[16];                         // raster block position
-  uint8_t v[64];                             // X | F2 | F3 | DC of the current block (see i4_pred_code)
-  uint8_t code[9][16];                       // shared-memory copy of i4_pred_code
 };
 
 __device__ __forceinline__ int f3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
