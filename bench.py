@@ -103,10 +103,17 @@ def cpu_quota():
         return None
 
 
+def usable_threads() -> int:
+    """All the host threads the container may really use: min(online CPUs, cgroup quota rounded up)."""
+    n = os.cpu_count() or 1
+    q = cpu_quota()
+    return max(1, min(n, int(q + 0.999))) if q else n
+
+
 def cpu_sample(frames, n_p: int, threads: int | None = None):
     """Oracle CSC + encode of 1 IDR + n_p P pictures on the host cores; returns (P frames/s, seconds, threads)."""
     import oracle
-    used = oracle.set_threads(threads or 0)
+    used = oracle.set_threads(threads or usable_threads())
     enc = oracle.RefEncoder(W, H)
     target = int(BITRATE_KBPS * 1000 / FPS_NOMINAL)
     enc.encode_bgra(frames[0], True, rc_mode=0, target_bits=target)
@@ -123,7 +130,7 @@ def run_reference(args, rank, world):
         return
     frames = synth_frames(min(N_DISTINCT, 4))
     import oracle
-    cores = oracle.set_threads(0)
+    cores = oracle.set_threads(usable_threads())
     enc = oracle.RefEncoder(W, H)
     target = int(BITRATE_KBPS * 1000 / FPS_NOMINAL)
     enc.encode_bgra(frames[0], True, rc_mode=0, target_bits=target)
