@@ -134,3 +134,36 @@ def test_scaled_encode_matches_oracle():
     for i, f in enumerate(frames):
         y, uv = oracle.csc_nv12(f, dst_w=dw, dst_h=dh, coded_w=enc.cw, coded_h=enc.ch)
         assert got[i].data == enc.encode_nv12(y, uv, i == 0, qp=29)
+
+
+def test_two_concurrent_sessions_are_independent():
+    """The reference keeps one capture instance per display (selkies.py:3178-3181): two sessions driven from two threads
+    on the same GPU must each produce exactly the stream a lone session produces."""
+    import threading
+    from selkies_b200 import _native as N
+    from selkies_b200.session import Session
+    cfgs = [(320, 192, 28, [synth.desktop(320, 192, t) for t in range(6)]), (256, 144, 33, [synth.bars(256, 144, t) for t in range(6)])]
+    solo = []
+    for w, h, qp, frames in cfgs:
+        with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=qp) as s:
+            for f in frames:
+                s.submit(f)
+            s.flush()
+            solo.append([g.data for g in s.take_frames()])
+    out = [None, None]
+
+    def worker(i):
+        w, h, qp, frames = cfgs[i]
+        with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=qp) as s:
+            for f in frames:
+                s.submit(f)
+                s.set_bitrate_kbps(5000 + i)          # control calls racing with submits must be harmless
+            s.flush()
+            out[i] = [g.data for g in s.take_frames()]
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert out[0] == solo[0] and out[1] == solo[1]
