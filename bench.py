@@ -124,6 +124,23 @@ def bind_to_gpu_numa_node(torch, device: int):
         return None
 
 
+def csc_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one 4K CSC launch, from the committed `ncu --set full` capture
+    (profiles/r1_ncu_full_raw.csv).  The 12.4 MB NV12 output stays in L2, so traffic ~= the 33.2 MB BGRA input."""
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_raw.csv"))))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if "csc_bgra_nv12" in r[ik]:
+                return float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1)
+    except Exception:
+        pass
+    return None
+
+
 def usable_threads() -> int:
     """All the host threads the container may really use: min(online CPUs, cgroup quota rounded up)."""
     n = os.cpu_count() or 1
@@ -336,7 +353,7 @@ def main():
     achieved = alg / (csc_ms * 1e-3) / 1e9 if csc_ms > 0 else 0.0
     burst_ms = sess.bench_csc_burst(N_DISTINCT, 200)
     roofline = {"bound": "hbm", "kernel": "csc_bgra_nv12_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": csc_dram_traffic(),
                 "algorithmic_bytes_per_launch": alg, "us_per_launch": csc_ms * 1e3,
                 "frac_of_8TBps_nominal": achieved / 8000.0,
                 "burst": {"note": "200 back-to-back launches between one event pair, same 8 cycled frames",
