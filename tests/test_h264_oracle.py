@@ -104,3 +104,10 @@ def test_cbr_rate_control_converges():
         sizes.append(len(au) * 8)
     avg = sum(sizes[10:]) / len(sizes[10:])
     assert 0.5 * target < avg < 1.6 * target
+
+
+def test_long_run_frame_num_wraps():
+    """frame_num is 8 bits (log2_max_frame_num_minus4 = 4): 600 pictures with an IDR in the middle still decode exactly."""
+    w, h = 64, 48
+    frames = [synth.desktop(w, h, t % 32) if t % 7 else synth.noise(w, h, t) for t in range(600)]
+    run(w, h, frames, 30, idr_at=(0, 300))
