@@ -1,6 +1,6 @@
 // h264_encoder.cu — host side of the H.264 Constrained-Baseline encoder: parameter sets (7.3.2.1/2),
 // HBM buffers, per-picture sequencing (frame_num, idr_pic_id, reference swap) and the kernel pipeline
-//   [k_intra_rows | k_inter_mb] -> k_cavlc_mb -> k_slice_bits -> k_pack_au
+//   [k_intra_rows | k_inter_mb] -> k_cavlc_mb -> k_slice_scan -> k_slice_copy -> k_slice_ep -> k_pack_au
 // The output format is what the reference's consumers require: Annex-B, CAVLC,
 // no B-frames, 4:2:0, in-band SPS/PPS on every IDR (src/selkies/rtc.py:394-401,
 // src/selkies/webrtc/codecs/h264.py:281-321).
@@ -13,8 +13,6 @@
 #include "h264_kernels.h"
 
 namespace b2v {
-
-int launch_pack_cap(const FrameCtx& f, long long au_cap, cudaStream_t st);
 
 static thread_local char g_enc_err[256] = "";
 const char* encoder_last_error() { return g_enc_err; }
