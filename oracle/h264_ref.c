@@ -628,10 +628,28 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     }
   uint8_t* ry = plane_y(e, e->cur);
   int cbp = 0;
+  /* coefficient decimation (encoder-side, as x264's dct-decimate): a block's score is 9 if any |level| > 1, else the sum
+   * over its +-1 levels of {3,2,2,1,1,1,0...}[zeros just below it in scan order]; an 8x8 quadrant whose four scores sum
+   * to < 4 is zeroed, and the whole luma when the macroblock total is < 6 — a few isolated +-1 cost more bits than they repair */
+  int score[16], s8[4] = {0, 0, 0, 0}, smb = 0;
   for (int b = 0; b < 16; b++) {
     int bx = blk_x[b] * 4, by = blk_y[b] * 4, res[16], dummy;
     for (int i = 0; i < 16; i++) { int p = (by + (i >> 2)) * 16 + bx + (i & 3); res[i] = cy[p] - py[p]; }
     tq4x4(res, qp, 0, 0, m->coef[1 + b], &dummy);
+    int sc = 0, zeros = 0, big = 0;
+    for (int k = 0; k < 16; k++) {
+      int v = m->coef[1 + b][k];
+      if (!v) { zeros++; continue; }
+      if (iabs(v) > 1) big = 1;
+      sc += zeros == 0 ? 3 : zeros <= 2 ? 2 : zeros <= 5 ? 1 : 0;
+      zeros = 0;
+    }
+    score[b] = big ? 9 : sc;
+    s8[b >> 2] += score[b]; smb += score[b];
+  }
+  for (int b = 0; b < 16; b++) {
+    int bx = blk_x[b] * 4, by = blk_y[b] * 4;
+    if (s8[b >> 2] < 4 || smb < 6) memset(m->coef[1 + b], 0, sizeof m->coef[1 + b]);
     int n = count_nz(m->coef[1 + b], 0, 16);
     m->nnz_l[blk_y[b] * 4 + blk_x[b]] = (uint8_t)n;
     if (n) cbp |= 1 << (b >> 2);

@@ -212,6 +212,31 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
 #pragma unroll
     for (int k = 0; k < 16; k++) lv[k] = 0;
   }
+  // ---- coefficient decimation of inter luma (oracle/h264_ref.c encode_inter_mb): block score = 9 if any
+  // |level| > 1, else sum over its +-1 levels of {3,2,2,1,1,1,0..}[zeros just below]; an 8x8 quadrant (lanes 4k..4k+3) scoring
+  // < 4 is zeroed, the whole luma when the macroblock scores < 6 ------------------------------------------------------
+  if (!INTRA16) {
+    int sc = 0;
+    if (is_luma) {
+      int zeros = 0; bool big = false;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int v = lv[k];
+        if (v == 0) { zeros++; }
+        else { big |= abs(v) > 1; sc += zeros == 0 ? 3 : zeros <= 2 ? 2 : zeros <= 5 ? 1 : 0; zeros = 0; }
+      }
+      if (big) sc = 9;
+    }
+    int s8 = sc + __shfl_xor_sync(FULL, sc, 1);
+    s8 += __shfl_xor_sync(FULL, s8, 2);
+    int smb = s8 + __shfl_xor_sync(FULL, s8, 4);
+    smb += __shfl_xor_sync(FULL, smb, 8);
+    if (is_luma && (s8 < 4 || smb < 6)) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) lv[k] = 0;
+      n = 0;
+    }
+  }
   // ---- DC paths -------------------------------------------------------------------------------
   int dc_deq = 0;
   if (INTRA16) {
