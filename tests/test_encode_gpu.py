@@ -163,3 +163,25 @@ def test_pixelflux_header_mode():
         assert d[0] == 0x04 and d[1] == (1 if i == 0 else 0)
         assert int.from_bytes(d[2:4], "big") == i and int.from_bytes(d[6:8], "big") == w and int.from_bytes(d[8:10], "big") == h
         assert d[10:14] == b"\x00\x00\x00\x01"
+
+
+def test_8k_encode_decodes_to_its_reconstruction():
+    """Maximum size the reference allows (7680x4320, selkies.py:281; level 6.2): property check instead of a full oracle run —
+    the stream decodes and the decoder output equals the encoder's reconstruction."""
+    w, h = 7680, 4320
+    tile = synth.desktop(1920, 1080, 0)
+    f0 = np.tile(tile, (4, 4, 1))
+    f1 = np.roll(f0, (6, -10), axis=(0, 1))
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=36) as s:
+        recs = []
+        for f in (f0, f1):
+            s.submit(f)
+            s.flush()
+            recs.append(s.recon())
+        got = s.take_frames()
+    assert got[0].is_key and not got[1].is_key
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert len(dec) == 2
+    for (Y, U, V), (ry, ruv) in zip(dec, recs):
+        assert np.array_equal(Y, ry[:h, :w]) and np.array_equal(U, ruv[: h // 2, 0:w:2]) and np.array_equal(V, ruv[: h // 2, 1:w:2])
+    assert len(got[1].data) < len(got[0].data) // 3          # the translation was found
