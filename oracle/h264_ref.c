@@ -959,6 +959,9 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   int mbs = e->mbw * e->mbh;
   if (rc_mode == 0 && e->rc_qp < 0) e->rc_qp = rc_initial_qp(target_bits, mbs);
   int qp = rc_mode == 1 ? clip3(0, 51, qp_fixed) : e->rc_qp;
+  /* CBR: an IDR requested in mid-stream (PLI, resize) is not coded finer than a fresh start with 4x the picture budget
+   * would be, which bounds the latency spike of the key frame */
+  if (rc_mode == 0 && idr) { int q0 = rc_initial_qp(4 * target_bits, mbs); if (qp < q0) qp = q0; }
   e->cur ^= 1;
   if (idr) { e->frame_num = 0; }
   /* phase A: analysis + reconstruction.  Intra: macroblocks of a slice are sequential (left/top

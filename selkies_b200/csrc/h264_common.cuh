@@ -70,7 +70,10 @@ __device__ __forceinline__ int rc_initial_qp(long long target_bits, int mbs) {
 __device__ __forceinline__ int frame_qp(const FrameCtx& f) {
   if (f.rc_mode == 1) return clip3i(0, 51, f.qp_fixed);
   int q = f.rc->qp;
-  return q < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : q;
+  if (q < 0) q = rc_initial_qp(f.target_bits, f.mbw * f.mbh);
+  // an IDR in mid-stream is not coded finer than a fresh start with 4x the picture budget would be (bounds the key-frame burst)
+  if (f.idr) q = max(q, rc_initial_qp(4 * f.target_bits, f.mbw * f.mbh));
+  return q;
 }
 __device__ __forceinline__ bool top_in_slice(const FrameCtx& f, int mby) { return (mby % f.slice_rows) != 0; }
 

@@ -493,7 +493,9 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
       if (total > cap) { ovf |= 2; total = cap; }
       h->size = (int32_t)total; h->qp = qp; h->is_idr = f.idr; h->n_slices = f.n_slices; h->total_bits = bits;
       h->overflow = ovf;
-      if (f.rc_mode == 0) rc_update_dev(f.rc, total * 8, f.target_bits, f.idr, qp);
+      // the controller evolves the running QP, not the (possibly raised) QP this picture was coded with
+      const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
+      if (f.rc_mode == 0) rc_update_dev(f.rc, total * 8, f.target_bits, f.idr, run_qp);
       h->next_qp = f.rc->qp;
       f.rc->last_qp = qp; f.rc->frames++;
     }

@@ -126,6 +126,16 @@ def test_cbr_rate_control_bit_exact():
     assert len({g.qp for g in got}) > 1          # the controller actually moved
 
 
+def test_cbr_midstream_idr_is_bounded_and_bit_exact():
+    """A key frame requested in mid-stream (PLI -> dynamic_idr_frame, rtc.py:601-603) is coded no finer than a fresh start
+    with 4x the picture budget; the controller then resumes from its running QP."""
+    w, h = 320, 192
+    frames = [synth.gradient(w, h, t) for t in range(14)]
+    got, ref, grec, rrec = encode_both(w, h, frames, rc_mode=N.B2V_RC_CBR, kbps=3000, fps=30.0, idr_at=(0, 9))
+    assert_same(got, ref, grec, rrec)
+    assert got[9].is_key and got[9].qp >= got[8].qp and got[10].qp <= got[9].qp
+
+
 def test_gpu_stream_decodes_to_its_reconstruction():
     w, h = 320, 184                               # cropped height
     frames = [synth.desktop(w, h, t) for t in range(4)]
