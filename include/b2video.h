@@ -97,6 +97,8 @@ typedef struct b2v_stats {
   int64_t kernel_launches;
   double  ms_csc, ms_intra, ms_inter, ms_cavlc, ms_slice, ms_pack, ms_total_gpu;
   int64_t n_csc, n_intra, n_inter, n_cavlc, n_slice, n_pack;
+  double  ms_csc_device;   /* same launches, timed by the kernel itself (%globaltimer: first block start .. last block end) */
+  int64_t n_csc_device;
 } b2v_stats;
 
 /* ---- lifecycle: replaces ScreenCapture() / start_capture / stop_capture

@@ -46,6 +46,7 @@ class B2VStats(C.Structure):
         ("ms_total_gpu", C.c_double),
         ("n_csc", C.c_int64), ("n_intra", C.c_int64), ("n_inter", C.c_int64),
         ("n_cavlc", C.c_int64), ("n_slice", C.c_int64), ("n_pack", C.c_int64),
+        ("ms_csc_device", C.c_double), ("n_csc_device", C.c_int64),
     ]
 
     def as_dict(self):

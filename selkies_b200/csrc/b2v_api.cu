@@ -77,6 +77,7 @@ struct Session {
   int out_next = 0;
   int ring_next = 0;
   cudaEvent_t ev_timer[2] = {};
+  unsigned long long* d_csc_ts = nullptr;     // [kMaxSlots][2] device stamps of the CSC launches (timing mode)
 
   // frame sequencing
   uint32_t frame_id = 0;
@@ -224,6 +225,10 @@ void output_loop(Session* s) {
       } else ms[5] = ms[0];
       std::lock_guard<std::mutex> lk(s->mu);
       s->stats.ms_csc += ms[0]; s->stats.n_csc++;
+      if (s->encode && size > 0) {
+        const AuHeader* ah2 = (const AuHeader*)s->h_out[j.out_idx];
+        if (ah2->csc_t1 > ah2->csc_t0 && ah2->csc_t0 != 0) { s->stats.ms_csc_device += (double)(ah2->csc_t1 - ah2->csc_t0) * 1e-6; s->stats.n_csc_device++; }
+      }
       if (s->encode) {
         if (j.is_key) { s->stats.ms_intra += ms[1]; s->stats.n_intra++; }
         else { s->stats.ms_inter += ms[1]; s->stats.n_inter++; }
@@ -285,13 +290,18 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
   }
   CscParams cp = csc_params(s, d_bgra, stride, s->d_cur);
   cudaEvent_t* ev = s->timing ? s->ev_t[out_idx] : nullptr;
+  if (ev && s->d_csc_ts && s->encode) {
+    cp.ts = s->d_csc_ts + 2 * out_idx;
+    cudaMemsetAsync(cp.ts, 0xFF, sizeof(unsigned long long), s->st_enc);
+    cudaMemsetAsync(cp.ts + 1, 0, sizeof(unsigned long long), s->st_enc);
+  }
   if (ev) cudaEventRecord(ev[0], s->st_enc);
   int nl = launch_csc(cp, s->sm_count, s->st_enc);
   if (ev) cudaEventRecord(ev[1], s->st_enc);
   if (in_slot >= 0) CK(cudaEventRecord(s->ev_csc[in_slot], s->st_enc));
   CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
   if (s->encode) {
-    fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = ev;
+    fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = ev; fp.csc_ts = cp.ts;
     nl += encoder_encode(s->enc, &fp, s->st_enc);
     CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
     CK(cudaStreamWaitEvent(s->st_out, s->ev_enc[out_idx], 0));
@@ -362,6 +372,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   }
   for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventCreate(&s->ev_t[i][k]);
   cudaEventCreate(&s->ev_timer[0]); cudaEventCreate(&s->ev_timer[1]);
+  if (s->timing) cudaMalloc((void**)&s->d_csc_ts, sizeof(unsigned long long) * 2 * kMaxSlots);
   int rc = alloc_geometry(s);
   if (rc) { free_geometry(s); delete s; return rc; }
   s->out_thread = std::thread(output_loop, s);
@@ -388,6 +399,7 @@ void b2v_destroy(void* h) {
   }
   for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventDestroy(s->ev_t[i][k]);
   cudaEventDestroy(s->ev_timer[0]); cudaEventDestroy(s->ev_timer[1]);
+  if (s->d_csc_ts) cudaFree(s->d_csc_ts);
   cudaStreamDestroy(s->st_copy); cudaStreamDestroy(s->st_enc); cudaStreamDestroy(s->st_out);
   delete s;
 }

@@ -22,6 +22,7 @@ struct CscParams {
   uint8_t* out_uv;      // coded_h/2 rows, pitch coded_w
   const Tap* tx;        // dst_w taps (null when 1:1)
   const Tap* ty;        // dst_h taps
+  unsigned long long* ts; // null, or {min block-start, max block-end} %globaltimer stamps of this launch (B2V_FLAG_TIMING)
 };
 
 // returns number of kernel launches issued (1)

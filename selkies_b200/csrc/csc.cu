@@ -67,8 +67,11 @@ __device__ __forceinline__ void convert_quad(const uint4& a, const uint4& b, uns
 template <int U>
 __global__ void __launch_bounds__(256) csc_bgra_nv12_fast(CscParams p, int quads, int pairs) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= quads) return;
-  const uint8_t* __restrict__ src = p.src + (size_t)q * 16;
+  if (p.ts && threadIdx.x == 0) {   // device-side stopwatch of this launch: first block start .. last block end
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); atomicMin(p.ts, t0);
+  }
+  const uint8_t* __restrict__ src = p.src + (size_t)(q < quads ? q : 0) * 16;
+  if (q < quads)
   for (int pr0 = blockIdx.y * U; pr0 < pairs; pr0 += gridDim.y * U) {
     uint4 a[U], b[U];
 #pragma unroll
@@ -91,6 +94,10 @@ __global__ void __launch_bounds__(256) csc_bgra_nv12_fast(CscParams p, int quads
         st_stream(p.out_uv + (size_t)pr * p.coded_w + q * 4, uv);
       }
     }
+  }
+  if (p.ts) {
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicMax(p.ts + 1, t1); }
   }
 }
 

@@ -56,6 +56,7 @@ struct FrameCtx {          // everything a kernel needs about the picture being 
   int* progress;           // [mbh] intra wavefront progress counters
   RcState* rc;
   const uint8_t* param_sets; int param_len;   // SPS+PPS NAL bytes (IDR pictures)
+  const unsigned long long* csc_ts;            // device stamps of this picture's CSC launch (or null)
   uint8_t* au;             // AuHeader + access unit
   int* overflow;
 };

@@ -189,7 +189,7 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   f.mbinfo = e->mbinfo; f.i4modes = e->i4modes; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
   f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
   f.slice_bits = e->slice_bits; f.progress = e->progress; f.rc = e->rc;
-  f.param_sets = e->param_sets; f.param_len = e->param_len; f.au = p->au; f.overflow = e->overflow;
+  f.param_sets = e->param_sets; f.param_len = e->param_len; f.csc_ts = p->csc_ts; f.au = p->au; f.overflow = e->overflow;
   int n = 0;
   n += idr ? launch_intra(f, st) : launch_inter(f, st);
   if (p->ev) cudaEventRecord(p->ev[2], st);

@@ -26,7 +26,8 @@ struct AuHeader {
   int64_t total_bits;      // before emulation prevention
   int32_t next_qp;         // rate controller output for the next frame
   int32_t overflow;        // non-zero if a macroblock exceeded its scratch budget (must never happen)
-  int32_t pad[8];
+  uint64_t csc_t0, csc_t1;  // %globaltimer stamps of the CSC launch of this picture (0 when timing is off)
+  int32_t pad[4];
 };
 static_assert(sizeof(AuHeader) == 64, "AuHeader must be 64 bytes");
 
@@ -38,6 +39,7 @@ struct EncodeFrameParams {
   int qp_fixed;
   int64_t target_bits;     // per frame, CBR
   cudaEvent_t* ev;         // null, or 8 timing events: encoder records ev[2..5] after each stage
+  const unsigned long long* csc_ts;   // null, or the CSC launch's device stamps to forward in the AuHeader
 };
 
 int  encoder_create(const EncoderConfig* cfg, Encoder** out);

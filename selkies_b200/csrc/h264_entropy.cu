@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
       const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
       if (f.rc_mode == 0) rc_update_dev(f.rc, total * 8, f.target_bits, f.idr, run_qp);
       h->next_qp = f.rc->qp;
+      h->csc_t0 = f.csc_ts ? f.csc_ts[0] : 0; h->csc_t1 = f.csc_ts ? f.csc_ts[1] : 0;
       f.rc->last_qp = qp; f.rc->frames++;
     }
   }
