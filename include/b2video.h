@@ -71,7 +71,8 @@ typedef struct b2v_settings {
 enum {
   B2V_FLAG_SPS_EVERY_IDR = 1,   /* in-band SPS/PPS before every IDR (rtc.py:394-401); always on */
   B2V_FLAG_NO_ENCODE     = 2,   /* CSC only (BASELINE config 4: 8K CSC roofline stress)         */
-  B2V_FLAG_TIMING        = 4    /* bracket every kernel with CUDA events (b2v_get_stats)        */
+  B2V_FLAG_TIMING        = 4,   /* bracket every kernel with CUDA events (b2v_get_stats)        */
+  B2V_FLAG_DEVICE_TIMER  = 8    /* with TIMING: the CSC kernel also stamps %globaltimer (ms_csc_device) */
 };
 
 /* One encoded frame, the native image of the pixelflux callback result

@@ -372,7 +372,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   }
   for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventCreate(&s->ev_t[i][k]);
   cudaEventCreate(&s->ev_timer[0]); cudaEventCreate(&s->ev_timer[1]);
-  if (s->timing) cudaMalloc((void**)&s->d_csc_ts, sizeof(unsigned long long) * 2 * kMaxSlots);
+  if (s->timing && (cfg->flags & B2V_FLAG_DEVICE_TIMER)) cudaMalloc((void**)&s->d_csc_ts, sizeof(unsigned long long) * 2 * kMaxSlots);
   int rc = alloc_geometry(s);
   if (rc) { free_geometry(s); delete s; return rc; }
   s->out_thread = std::thread(output_loop, s);
