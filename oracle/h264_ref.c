@@ -26,7 +26,8 @@
  *   - P pictures: every macroblock P_L0_16x16 (coded as P_Skip when mv == skip predictor and cbp == 0);
  *     full-pel exhaustive search dx in [-16,15], dy in [-16,16] against the previous reconstruction
  *     (coordinates clamped to the coded picture), cost = SAD + lambda(qp)*(bits_se(4dx)+bits_se(4dy)),
- *     argmin of (cost << 11 | (dy+16)*32 + (dx+16)); the search is skipped (mv = 0) when SAD(0,0) <= 96*lambda(qp)
+ *     argmin of (cost << 11 | (dy+16)*32 + (dx+16)); the search is skipped (mv = 0) when SAD(0,0) <= 96*lambda(qp);
+ *     then half- and quarter-sample refinement (6-tap interpolation, 8 + 8 candidates) around the full-sample winner
  *   - quantisation: |l| = (|w|*MF + f) >> (15+qp/6), f = 2^(15+qp/6)/3 intra, /6 inter, |l| clamped to 2047
  *   - constant QP inside a picture; picture QP from the frame-level rate controller below
  */
@@ -574,7 +575,41 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
 
 /* ------------------------------------------------------------------ inter macroblock (8.4) */
 #define ME_EARLY_SAD_PER_LAMBDA 96
+#define ME_FRAC_PENALTY_BITS 4   /* fractional vectors pay 4 extra bits: they cost more mvd bits than the zero-relative estimate sees */
 static int se_bits(int v) { unsigned c = v > 0 ? 2u * v - 1 : (unsigned)(-2 * v); int len = 0; c += 1; while ((c >> len) > 1) len++; return 2 * len + 1; }
+
+/* 8.4.2.2.1: predicted 16x16 luma block for a quarter-sample offset (qx,qy) in [-3,3] from the full-sample position the
+ * planes were built around.  Every fractional position is one plane or the rounded average of two (Table 8-12):
+ *   G integer, b horizontal half, h vertical half, j centre; a,c,d,n,e,f,g,i,k,p,q,r = averages. */
+static void luma_mc_planes(uint8_t Gp[22][22], uint8_t bq[18][17], uint8_t hq[17][18], uint8_t jq[17][17], int qx, int qy, uint8_t out[256]) {
+  const int xi = asr(qx, 2), yi = asr(qy, 2), fx = qx & 3, fy = qy & 3;
+  for (int y = 0; y < 16; y++)
+    for (int x = 0; x < 16; x++) {
+      const int X = x + xi, Y = y + yi;
+      const int G = Gp[Y + 3][X + 3], H = Gp[Y + 3][X + 4], M = Gp[Y + 4][X + 3];
+      const int b = bq[Y + 1][X + 1], s = bq[Y + 2][X + 1], h = hq[Y + 1][X + 1], mm = hq[Y + 1][X + 2], j = jq[Y + 1][X + 1];
+      int v;
+      switch (fy * 4 + fx) {
+        case 0: v = G; break;
+        case 1: v = (G + b + 1) >> 1; break;
+        case 2: v = b; break;
+        case 3: v = (H + b + 1) >> 1; break;
+        case 4: v = (G + h + 1) >> 1; break;
+        case 5: v = (b + h + 1) >> 1; break;
+        case 6: v = (b + j + 1) >> 1; break;
+        case 7: v = (b + mm + 1) >> 1; break;
+        case 8: v = h; break;
+        case 9: v = (h + j + 1) >> 1; break;
+        case 10: v = j; break;
+        case 11: v = (j + mm + 1) >> 1; break;
+        case 12: v = (M + h + 1) >> 1; break;
+        case 13: v = (h + s + 1) >> 1; break;
+        case 14: v = (j + s + 1) >> 1; break;
+        default: v = (mm + s + 1) >> 1; break;
+      }
+      out[y * 16 + x] = (uint8_t)v;
+    }
+}
 
 static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
   mb_t* m = &e->mbs[mby * e->mbw + mbx];
@@ -608,13 +643,55 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
       uint32_t key = (cost << 11) | (uint32_t)((dy + 16) * 32 + (dx + 16));
       if (key < best) { best = key; bdx = dx; bdy = dy; }
     }
-  m->mv[0] = (int16_t)(4 * bdx); m->mv[1] = (int16_t)(4 * bdy);
-  /* prediction: luma full-sample copy (8.4.2.2.1 with zero fractions); chroma bilinear 1/8 (8.4.2.2.2) */
+  /* ---- quarter-sample refinement (8.4.2.2.1).  Around the best full-sample position (only when its 6-tap support
+   * [-3,+18] lies inside the 48x48 window, i.e. |dx|,|dy| <= 13, and the search ran): the half-sample planes
+   *   b1 = E - 5F + 20G + 20H - 5I + J (unrounded), b = clip((b1+16)>>5), h likewise vertically, j = clip((6-tap of b1 + 512)>>10)
+   * are built once; stage H tries the 8 half-sample neighbours, stage Q the 8 quarter-sample neighbours of the stage-H
+   * winner; cost = SAD + lambda*(bits(mvx)+bits(mvy) + 4 if fractional), key = cost<<4 | candidate index (0 = centre wins ties). */
+  int mvx = 4 * bdx, mvy = 4 * bdy;
   uint8_t py[256], pc[2][64];
-  for (int r = 0; r < 16; r++)
-    for (int c = 0; c < 16; c++) py[r * 16 + c] = refy[(size_t)clip3(0, e->ch - 1, y0 + bdy + r) * e->cw + clip3(0, e->cw - 1, x0 + bdx + c)];
-  int mvcx = 4 * bdx, mvcy = 4 * bdy, xi = mvcx >> 3, yi = mvcy >> 3, xf = mvcx & 7, yf = mvcy & 7;   /* >> on negatives: floor (checked in asr form below) */
-  xi = asr(mvcx, 3); yi = asr(mvcy, 3);
+  int have_planes = 0;
+  static const int8_t nb8[8][2] = { {-1,-1}, {0,-1}, {1,-1}, {-1,0}, {1,0}, {-1,1}, {0,1}, {1,1} };
+  uint8_t Gp[22][22], bq[18][17], hq[17][18], jq[17][17];   /* Gp[v+3][u+3], bq[v+1][u+1], hq[v+1][u+1], jq[v+1][u+1] */
+  if (search && iabs(bdx) <= 13 && iabs(bdy) <= 13) {
+    int16_t b1[22][17];
+    const int ox = 16 + bdx, oy = 16 + bdy;
+    for (int v = -3; v <= 18; v++) for (int u = -3; u <= 18; u++) Gp[v + 3][u + 3] = win[oy + v][ox + u];
+#define GW(u, v) ((int)Gp[(v) + 3][(u) + 3])
+    for (int v = -3; v <= 18; v++)
+      for (int u = -1; u <= 15; u++) b1[v + 3][u + 1] = (int16_t)(GW(u - 2, v) - 5 * GW(u - 1, v) + 20 * GW(u, v) + 20 * GW(u + 1, v) - 5 * GW(u + 2, v) + GW(u + 3, v));
+    for (int v = -1; v <= 16; v++) for (int u = -1; u <= 15; u++) bq[v + 1][u + 1] = (uint8_t)clip1((b1[v + 3][u + 1] + 16) >> 5);
+    for (int v = -1; v <= 15; v++)
+      for (int u = -1; u <= 16; u++)
+        hq[v + 1][u + 1] = (uint8_t)clip1((GW(u, v - 2) - 5 * GW(u, v - 1) + 20 * GW(u, v) + 20 * GW(u, v + 1) - 5 * GW(u, v + 2) + GW(u, v + 3) + 16) >> 5);
+    for (int v = -1; v <= 15; v++)
+      for (int u = -1; u <= 15; u++)
+        jq[v + 1][u + 1] = (uint8_t)clip1((b1[v + 1][u + 1] - 5 * b1[v + 2][u + 1] + 20 * b1[v + 3][u + 1] + 20 * b1[v + 4][u + 1] - 5 * b1[v + 5][u + 1] + b1[v + 6][u + 1] + 512) >> 10);
+    have_planes = 1;
+    int cx = 0, cyq = 0;                      /* offset from the full-sample position, quarter units */
+    for (int stage = 0; stage < 2; stage++) {
+      const int step = stage == 0 ? 2 : 1;
+      uint32_t bestk = 0xffffffffu; int bi = 0;
+      for (int i = 0; i <= 8; i++) {
+        const int qx = cx + (i ? nb8[i - 1][0] * step : 0), qy = cyq + (i ? nb8[i - 1][1] * step : 0);
+        uint8_t pr[256];
+        luma_mc_planes(Gp, bq, hq, jq, qx, qy, pr);
+        const uint32_t cost = (uint32_t)(sad_n(cy, pr, 256) + lambda * (se_bits(4 * bdx + qx) + se_bits(4 * bdy + qy) + (((qx | qy) & 3) ? ME_FRAC_PENALTY_BITS : 0)));
+        const uint32_t key = (cost << 4) | (uint32_t)i;
+        if (key < bestk) { bestk = key; bi = i; }
+      }
+      if (bi) { cx += nb8[bi - 1][0] * step; cyq += nb8[bi - 1][1] * step; }
+    }
+    mvx += cx; mvy += cyq;
+    luma_mc_planes(Gp, bq, hq, jq, cx, cyq, py);
+#undef GW
+  }
+  m->mv[0] = (int16_t)mvx; m->mv[1] = (int16_t)mvy;
+  /* prediction: luma from the planes above, or a full-sample copy; chroma bilinear 1/8 (8.4.2.2.2) */
+  if (!have_planes)
+    for (int r = 0; r < 16; r++)
+      for (int c = 0; c < 16; c++) py[r * 16 + c] = refy[(size_t)clip3(0, e->ch - 1, y0 + bdy + r) * e->cw + clip3(0, e->cw - 1, x0 + bdx + c)];
+  int mvcx = mvx, mvcy = mvy, xi = asr(mvcx, 3), yi = asr(mvcy, 3), xf = mvcx & 7, yf = mvcy & 7;
   int cwc = e->cw / 2, chc = e->ch / 2;
   for (int r = 0; r < 8; r++)
     for (int c = 0; c < 8; c++) {

@@ -7,7 +7,10 @@
 //     pairs it belongs to — 33 SAD accumulators live in registers, VABSDIFF4.U8.ACC does 4 pixels per
 //     instruction; cost = SAD + lambda*(bits(mvx)+bits(mvy)); the arg-min is a single warp-wide
 //     REDUX.MIN over (cost << 11 | candidate index);
-//  3. prediction (luma copy, chroma 1/8-sample bilinear), residual transform/quantisation and
+//  3. quarter-sample refinement: the half-sample planes (6-tap) around the winner are built in shared memory, every
+//     fractional position is one plane row or the byte-wise rounded average of two (Table 8-12 as data, __vavgu4), 8 half-
+//     then 8 quarter-sample candidates are scored with VABSDIFF4 on whole rows (lane = candidate half x row);
+//  4. prediction (luma from the planes, chroma 1/8-sample bilinear), residual transform/quantisation and
 //     reconstruction with one lane per 4x4 block (h264_common.cuh).
 // There is no dependency between macroblocks of a P picture: motion-vector prediction and the P_Skip
 // decision only matter for entropy coding and are resolved in h264_entropy.cu.
@@ -21,10 +24,56 @@ constexpr int WIN_ROWS = 48, WIN_WORDS = 12;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int ME_EARLY_SAD_PER_LAMBDA = 96;   // skip the search when SAD(0,0) <= 96 * lambda(qp)
 
-struct InterSm {
+struct alignas(16) InterSm {      // one per warp; the 16-byte size padding keeps t's uint4 accesses aligned for every array element
   MbTile t;
   uint32_t win[WIN_ROWS][WIN_WORDS];
+  // quarter-sample refinement (8.4.2.2.1): planes around the best full-sample position, sample (X,Y) relative to it
+  alignas(4) int16_t b1[22][18];   // unrounded horizontal 6-tap, b1[Y+3][X+1], Y in [-3,18], X in [-1,15]
+  alignas(4) uint8_t bq[18][24];   // b = clip((b1+16)>>5),          bq[Y+1][X+1], Y in [-1,16], X in [-1,15]
+  alignas(4) uint8_t hq[17][24];   // vertical half sample,          hq[Y+1][X+1], Y in [-1,15], X in [-1,16]
+  alignas(4) uint8_t jq[17][24];   // centre half sample,            jq[Y+1][X+1], Y,X in [-1,15]
 };
+
+constexpr int ME_FRAC_PENALTY_BITS = 4;   // fractional vectors pay 4 extra bits in the refinement cost
+
+// Table 8-12 as data: every fractional position is one plane sample or the rounded average of two.
+// entry = p1 | dx1<<2 | dy1<<3 | p2<<4 | dx2<<7 | dy2<<8, planes 0 G (full sample), 1 b, 2 h, 3 j, p2 = 4: none
+__device__ const uint16_t subpel_tab[16] = {
+  /* fy=0 */ 0 | (4 << 4),            0 | (1 << 4),             1 | (4 << 4),            0 | (1 << 2) | (1 << 4),
+  /* fy=1 */ 0 | (2 << 4),            1 | (2 << 4),             1 | (3 << 4),            1 | (2 << 4) | (1 << 7),
+  /* fy=2 */ 2 | (4 << 4),            2 | (3 << 4),             3 | (4 << 4),            3 | (2 << 4) | (1 << 7),
+  /* fy=3 */ 0 | (1 << 3) | (2 << 4), 2 | (1 << 4) | (1 << 8),  3 | (1 << 4) | (1 << 8), 2 | (1 << 2) | (1 << 4) | (1 << 8),
+};
+
+__device__ __forceinline__ int se_bits_dev(int v) {
+  const unsigned c = (v > 0 ? 2u * (unsigned)v - 1u : (unsigned)(-2 * v)) + 1u;
+  return 2 * (31 - __clz(c)) + 1;
+}
+// 16 consecutive bytes starting at an arbitrarily aligned shared-memory address -> 4 words
+__device__ __forceinline__ void load_row16(const uint8_t* p, uint32_t out[4]) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  const int sh = (a & 3) * 8;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p - (a & 3));
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  out[0] = __funnelshift_r(w0, w1, sh); out[1] = __funnelshift_r(w1, w2, sh); out[2] = __funnelshift_r(w2, w3, sh); out[3] = __funnelshift_r(w3, w4, sh);
+}
+__device__ __forceinline__ const uint8_t* plane_ptr(const InterSm& sm, int plane, int ox, int oy, int X, int Y) {
+  return plane == 0 ? reinterpret_cast<const uint8_t*>(&sm.win[oy + Y][0]) + ox + X
+       : plane == 1 ? &sm.bq[Y + 1][X + 1] : plane == 2 ? &sm.hq[Y + 1][X + 1] : &sm.jq[Y + 1][X + 1];
+}
+// predicted luma row `row` (16 samples) for the quarter-sample offset (qx,qy) in [-3,3] from the full-sample position (ox,oy)
+__device__ __forceinline__ void subpel_row(const InterSm& sm, int ox, int oy, int qx, int qy, int row, uint32_t out[4]) {
+  const int xi = qx >> 2, yi = qy >> 2;
+  const uint32_t e = subpel_tab[(qy & 3) * 4 + (qx & 3)];
+  load_row16(plane_ptr(sm, e & 3, ox, oy, xi + ((e >> 2) & 1), row + yi + ((e >> 3) & 1)), out);
+  const int p2 = (e >> 4) & 7;
+  if (p2 < 4) {
+    uint32_t o2[4];
+    load_row16(plane_ptr(sm, p2, ox, oy, xi + ((e >> 7) & 1), row + yi + ((e >> 8) & 1)), o2);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = __vavgu4(out[k], o2[k]);      // (a + b + 1) >> 1 per byte
+  }
+}
 
 __device__ __forceinline__ uint32_t sad4acc(uint32_t a, uint32_t b, uint32_t c) {   // VABSDIFF4.U8.ACC with a live accumulator
   uint32_t d; asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
@@ -95,7 +144,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     const int sad0 = __reduce_add_sync(FULL, (int)s0);
     if (sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda) best = 0xffffffffu;
   }
-  if (best == 0xffffffffu) {
+  const bool searched = best == 0xffffffffu;
+  if (searched) {
   // ---- exhaustive search ---------------------------------------------------------------------------
   uint32_t c[16][4];
 #pragma unroll
@@ -130,16 +180,87 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   }
   const int dyi = (best & 2047) >> 5, dxi = best & 31, dx = dxi - 16, dy = dyi - 16;
 
+  // ---- quarter-sample refinement (oracle/h264_ref.c encode_inter_mb) ---------------------------------
+  int mvx = 4 * dx, mvy = 4 * dy;
+  const bool refine = searched && abs(dx) <= 13 && abs(dy) <= 13;     // 6-tap support [-3,+18] inside the 48x48 window
+  const int ox = dxi, oy = dyi;                                        // window coordinates of the full-sample position
+  if (refine) {
+    // half-sample planes
+    for (int i = lane; i < 22 * 17; i += 32) {
+      const int v = i / 17, u = i - v * 17;                             // row Y = v-3, column X = u-1
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(&sm.win[oy + v - 3][0]) + ox + u - 1;
+      sm.b1[v][u] = (int16_t)((int)g[-2] - 5 * (int)g[-1] + 20 * (int)g[0] + 20 * (int)g[1] - 5 * (int)g[2] + (int)g[3]);
+    }
+    for (int i = lane; i < 17 * 18; i += 32) {
+      const int v = i / 18, u = i - v * 18;                             // Y = v-1, X = u-1
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(&sm.win[oy + v - 1][0]) + ox + u - 1;
+      const int h1 = (int)g[-2 * 48] - 5 * (int)g[-48] + 20 * (int)g[0] + 20 * (int)g[48] - 5 * (int)g[2 * 48] + (int)g[3 * 48];
+      sm.hq[v][u] = (uint8_t)clip255((h1 + 16) >> 5);
+    }
+    __syncwarp();
+    for (int i = lane; i < 18 * 17; i += 32) {
+      const int v = i / 17, u = i - v * 17;                             // Y = v-1 -> b1 row v+2
+      sm.bq[v][u] = (uint8_t)clip255(((int)sm.b1[v + 2][u] + 16) >> 5);
+    }
+    for (int i = lane; i < 17 * 17; i += 32) {
+      const int v = i / 17, u = i - v * 17;                             // Y = v-1 -> b1 rows v..v+5
+      const int j1 = (int)sm.b1[v][u] - 5 * (int)sm.b1[v + 1][u] + 20 * (int)sm.b1[v + 2][u] + 20 * (int)sm.b1[v + 3][u] - 5 * (int)sm.b1[v + 4][u] + (int)sm.b1[v + 5][u];
+      sm.jq[v][u] = (uint8_t)clip255((j1 + 512) >> 10);
+    }
+    __syncwarp();
+    // stage H (half-sample neighbours), stage Q (quarter-sample neighbours of the stage-H winner)
+    int cx = 0, cyq = 0;
+    uint32_t centre_cost = best >> 11;
+    const int half = lane >> 4, row = lane & 15;
+    const uint4 cur4 = *reinterpret_cast<const uint4*>(&t.cur_y[row][0]);
+#pragma unroll 1
+    for (int stage = 0; stage < 2; stage++) {
+      const int step = stage == 0 ? 2 : 1;
+      uint32_t bestk = (centre_cost << 4);                              // candidate 0 = centre
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) {
+        const int cand = 2 * k + half;                                  // 0..7 in the order of nb8[]
+        const int nx = cand < 3 ? cand - 1 : cand == 3 ? -1 : cand == 4 ? 1 : cand - 6;
+        const int ny = cand < 3 ? -1 : cand < 5 ? 0 : 1;
+        const int qx = cx + nx * step, qy = cyq + ny * step;
+        uint32_t pr[4];
+        subpel_row(sm, ox, oy, qx, qy, row, pr);
+        int sad = (int)sad4acc(cur4.x, pr[0], sad4acc(cur4.y, pr[1], sad4acc(cur4.z, pr[2], sad4acc(cur4.w, pr[3], 0u))));
+        sad += __shfl_xor_sync(FULL, sad, 1); sad += __shfl_xor_sync(FULL, sad, 2);
+        sad += __shfl_xor_sync(FULL, sad, 4); sad += __shfl_xor_sync(FULL, sad, 8);
+        const uint32_t cost = (uint32_t)(sad + lambda * (se_bits_dev(4 * dx + qx) + se_bits_dev(4 * dy + qy) + (((qx | qy) & 3) ? ME_FRAC_PENALTY_BITS : 0)));
+        uint32_t key = (cost << 4) | (uint32_t)(cand + 1);
+        key = min(key, __shfl_xor_sync(FULL, key, 16));
+        bestk = min(bestk, key);
+      }
+      const int bi = bestk & 15;
+      if (bi) {
+        const int cand = bi - 1;
+        cx += (cand < 3 ? cand - 1 : cand == 3 ? -1 : cand == 4 ? 1 : cand - 6) * step;
+        cyq += (cand < 3 ? -1 : cand < 5 ? 0 : 1) * step;
+        centre_cost = bestk >> 4;
+      }
+    }
+    mvx += cx; mvy += cyq;
+    if (lane < 16) {
+      uint32_t pr[4];
+      subpel_row(sm, ox, oy, cx, cyq, lane, pr);
+      *reinterpret_cast<uint4*>(&t.pred_y[lane][0]) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+    }
+  }
+
   // ---- prediction ------------------------------------------------------------------------------------
   {
-    const uint8_t* wb = reinterpret_cast<const uint8_t*>(&sm.win[dyi + r8][0]) + dxi + c8;
-    uint32_t p0 = 0, p1 = 0;
+    if (!refine) {
+      const uint8_t* wb = reinterpret_cast<const uint8_t*>(&sm.win[dyi + r8][0]) + dxi + c8;
+      uint32_t p0 = 0, p1 = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) { p0 |= (uint32_t)wb[j] << (8 * j); p1 |= (uint32_t)wb[4 + j] << (8 * j); }
-    *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = p0;
-    *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = p1;
-    // chroma: mvC = (4dx, 4dy) in 1/8 chroma samples (8.4.1.4, 8.4.2.2.2)
-    const int xi = dx >> 1, yi = dy >> 1, xf = (dx & 1) * 4, yf = (dy & 1) * 4;
+      for (int j = 0; j < 4; j++) { p0 |= (uint32_t)wb[j] << (8 * j); p1 |= (uint32_t)wb[4 + j] << (8 * j); }
+      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = p0;
+      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = p1;
+    }
+    // chroma: mvC = luma mv, in 1/8 chroma samples (8.4.1.4, 8.4.2.2.2)
+    const int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
     const int cwc = f.cw >> 1, chc = f.ch >> 1;
     const int ya = clip3i(0, chc - 1, mby * 8 + yi + rc4), yb = clip3i(0, chc - 1, mby * 8 + yi + rc4 + 1);
     uint32_t out = 0;
@@ -172,7 +293,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
       *reinterpret_cast<uint2*>(f.recon + ysz + (size_t)(mby * 8 + r8) * f.cw + x0 + c8) = w;
     }
     if (lane == 0) {
-      MbInfo mi; mi.mvx = (int16_t)(4 * dx); mi.mvy = (int16_t)(4 * dy); mi.type = MB_P16; mi.i16_mode = 0; mi.chroma_mode = 0; mi.cbp = (uint8_t)cbp;
+      MbInfo mi; mi.mvx = (int16_t)mvx; mi.mvy = (int16_t)mvy; mi.type = MB_P16; mi.i16_mode = 0; mi.chroma_mode = 0; mi.cbp = (uint8_t)cbp;
       if (cbp < 0) { mi.mvx = 0; mi.mvy = 0; mi.type = MB_PCM; mi.cbp = 0; }   // too big for CAVLC: I_PCM (transform_mb)
       f.mbinfo[mb] = mi;
     }
