@@ -111,6 +111,25 @@ def test_intra4x4_bit_exact(slice_rows, qp):
     assert np.array_equal(dec[2][0], grec[0][:h, :w])
 
 
+def test_subpel_motion_bit_exact():
+    """A pan by (1.37, 0.61) samples per picture: the quarter-sample refinement (6-tap interpolation) must be taken and must
+    match the oracle; the P pictures cost a fraction of what integer-only vectors would need."""
+    cv2 = pytest.importorskip("cv2")
+    w, h = 320, 192
+    rng = np.random.default_rng(5)
+    big = cv2.GaussianBlur(rng.normal(0, 1, (h + 96, w + 96, 3)).astype(np.float32), (0, 0), 5) * 900 + \
+        cv2.GaussianBlur(rng.normal(0, 1, (h + 96, w + 96, 3)).astype(np.float32), (0, 0), 1.2) * 40 + 128
+    frames = []
+    for t in range(5):
+        a = cv2.warpAffine(big, np.float32([[1, 0, -(24 + 1.37 * t)], [0, 1, -(24 + 0.61 * t)]]), (w, h), flags=cv2.INTER_CUBIC)
+        frames.append(np.dstack([np.clip(a, 0, 255).astype(np.uint8), np.full((h, w), 255, np.uint8)]))
+    got, ref, grec, rrec = encode_both(w, h, frames, qp=26, slice_rows=2)
+    assert_same(got, ref, grec, rrec)
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert np.array_equal(dec[4][0], grec[0][:h, :w])
+    assert sum(len(g.data) for g in got[1:]) < 4 * len(got[0].data) // 3      # 4 P pictures well under 1.33 IDR
+
+
 def test_static_scene_is_skipped():
     f = synth.desktop(320, 192, 0)
     got, ref, grec, rrec = encode_both(320, 192, [f, f, f], qp=30)
