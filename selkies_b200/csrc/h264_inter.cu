@@ -182,7 +182,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
 
   // ---- quarter-sample refinement (oracle/h264_ref.c encode_inter_mb) ---------------------------------
   int mvx = 4 * dx, mvy = 4 * dy;
-  const bool refine = searched && abs(dx) <= 13 && abs(dy) <= 13;     // 6-tap support [-3,+18] inside the 48x48 window
+  // refine only inside the window (6-tap support [-3,+18]) and when the full-sample match is not already within the
+  // quantisation noise of this QP (same threshold as the zero-motion early termination)
+  const int sad_int = searched ? (int)(best >> 11) - lambda * (se_bits_dev(4 * dx) + se_bits_dev(4 * dy)) : 0;
+  const bool refine = searched && abs(dx) <= 13 && abs(dy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda;
   const int ox = dxi, oy = dyi;                                        // window coordinates of the full-sample position
   if (refine) {
     // half-sample planes
