@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B2V_ABI_VERSION 1
+#define B2V_ABI_VERSION 2
 
 enum {
   B2V_OK = 0,
@@ -65,7 +65,17 @@ typedef struct b2v_settings {
   int32_t header_mode;      /* B2V_HDR_*                                                    */
   int32_t ring_slots;       /* pinned BGRA ingest ring depth (2..16); 0 = default 4          */
   int32_t flags;            /* B2V_FLAG_*                                                   */
-  int32_t reserved[4];
+  int32_t paintover_trigger_frames; /* CQP mode: after this many consecutive all-skipped pictures code ONE picture at
+                                       paintover_crf (CaptureSettings.paint_over_trigger_frames / use_paint_over_quality,
+                                       selkies.py:3226-3229); 0 = off */
+  int32_t paintover_crf;            /* CaptureSettings.h264_paintover_crf */
+  int32_t stripe_rows;      /* striped mode (CaptureSettings.h264_fullframe = False, selkies.py:3219; encoder
+                               "x264enc-striped"): macroblock rows per stripe, a multiple of slice_rows.  Every stripe is
+                               an independent H.264 stream (own SPS/PPS, own frame_num, motion confined to the stripe)
+                               delivered by its own callback with y_start/height (10-byte header bytes 4..9,
+                               selkies-ws-core.js:3183-3196); a stripe whose macroblocks were all skipped is not
+                               delivered.  0 or >= picture rows = full frame */
+  int32_t reserved[1];
 } b2v_settings;
 
 enum {
@@ -86,6 +96,8 @@ typedef struct b2v_frame {
   int32_t  qp;           /* slice QP used for this frame                     */
   int64_t  pts90k;       /* frame_id * (90000 // fps)  (media_pipeline.py:291-292) */
   int64_t  capture_ns;   /* value passed to b2v_ring_submit                  */
+  int32_t  y_start;      /* first picture row of this stripe (0 when full-frame)           */
+  int32_t  height;       /* visible rows in this stripe (the picture height when full-frame) */
 } b2v_frame;
 
 typedef void (*b2v_cb)(const b2v_frame* frame, void* user);

@@ -89,6 +89,26 @@ class RefEncoder:
         self.h = C.c_void_p(L.b2v_ref_enc_create(width, height, slice_rows))
         self.cw, self.ch = L.b2v_ref_enc_coded_w(self.h), L.b2v_ref_enc_coded_h(self.h)
         self._out = np.empty(L.b2v_ref_enc_max_au(self.h), np.uint8)
+        L.b2v_ref_enc_set_paintover.argtypes = [C.c_void_p, C.c_int, C.c_int]
+
+    def set_stripes(self, stripe_rows: int) -> int:
+        """Striped mode: bands of `stripe_rows` macroblock rows, each an independent stream.  Returns the band count."""
+        self.L.b2v_ref_enc_set_stripes.argtypes = [C.c_void_p, C.c_int]
+        n = self.L.b2v_ref_enc_set_stripes(self.h, stripe_rows)
+        if n < 0:
+            raise ValueError("stripe_rows must be a multiple of slice_rows")
+        self.stripe_rows = stripe_rows if n > 1 else 0
+        return n
+
+    def stripe_table(self):
+        """[(offset, size, coded)] per band for the last picture (empty when striping is off)."""
+        t = np.zeros(512 * 3, np.int32)
+        self.L.b2v_ref_enc_stripe_table.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        n = self.L.b2v_ref_enc_stripe_table(self.h, t.ctypes.data_as(C.POINTER(C.c_int32)))
+        return [tuple(int(v) for v in t[3 * i: 3 * i + 3]) for i in range(n)]
+
+    def set_paintover(self, trigger_frames: int, qp: int) -> None:
+        self.L.b2v_ref_enc_set_paintover(self.h, trigger_frames, qp)
 
     def encode_nv12(self, y: np.ndarray, uv: np.ndarray, idr: bool, rc_mode: int = 1, qp: int = 26, target_bits: int = 0) -> bytes:
         assert y.shape == (self.ch, self.cw) and uv.shape == (self.ch // 2, self.cw)

@@ -92,6 +92,7 @@ typedef struct {
   int8_t  i4_modes[16];   /* Intra4x4PredMode per 4x4 block, raster y*4+x (type 3 only) */
 } mb_t;
 
+#define MAX_STRIPES 512
 typedef struct {
   int width, height, cw, ch, mbw, mbh, slice_rows, n_slices;
   uint8_t* recon[2];      /* NV12, coded size; recon[cur] is being written, recon[cur^1] is the reference */
@@ -100,8 +101,15 @@ typedef struct {
   int frame_num, idr_count;
   /* rate controller */
   int rc_qp; int64_t rc_fullness;
+  int static_run, paint_trigger, paint_qp;   /* CQP paint-over: one finer picture after `paint_trigger` all-skipped pictures */
   int last_qp; int64_t last_bits;
   uint8_t sps[64], pps[32]; int sps_len, pps_len;
+  /* striped mode (pixelflux h264_fullframe = False): the picture is cut into bands of stripe_rows macroblock rows, each an
+   * independent H.264 stream (own SPS, own frame_num, motion vectors confined to the band by reference-sample clamping) */
+  int stripe_rows, n_stripes;
+  int stripe_fn[MAX_STRIPES];
+  int32_t stripe_tab[MAX_STRIPES][3];   /* last picture: byte offset, size, coded flag */
+  uint8_t sps_band[2][64]; int sps_band_len[2];   /* [0] regular band, [1] last band (may be shorter / cropped) */
 } enc_t;
 
 static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -112,21 +120,20 @@ static int asr(int v, int s) { return v >= 0 ? (v >> s) : -((-v + (1 << s) - 1) 
 static int level_idc_for(int mbs) { return mbs <= 3600 ? 31 : mbs <= 8704 ? 42 : mbs <= 22080 ? 51 : mbs <= 36864 ? 52 : 62; }
 
 /* 7.3.2.1 SPS, 7.3.2.2 PPS */
-static void write_param_sets(enc_t* e) {
+static int build_sps(uint8_t* dst, int mbw, int mbh, int crop_r, int crop_b) {
   bitw_t b; bw_init(&b);
   bw_put(&b, 8, 66);            /* profile_idc Baseline */
   bw_put(&b, 8, 0xC0);          /* constraint_set0_flag, constraint_set1_flag => Constrained Baseline */
-  bw_put(&b, 8, level_idc_for(e->mbw * e->mbh));
+  bw_put(&b, 8, level_idc_for(mbw * mbh));
   bw_ue(&b, 0);                 /* seq_parameter_set_id */
   bw_ue(&b, 4);                 /* log2_max_frame_num_minus4 => frame_num is 8 bits */
   bw_ue(&b, 2);                 /* pic_order_cnt_type 2: output order == decoding order */
   bw_ue(&b, 1);                 /* max_num_ref_frames */
   bw_put(&b, 1, 0);             /* gaps_in_frame_num_value_allowed_flag */
-  bw_ue(&b, e->mbw - 1);
-  bw_ue(&b, e->mbh - 1);
+  bw_ue(&b, mbw - 1);
+  bw_ue(&b, mbh - 1);
   bw_put(&b, 1, 1);             /* frame_mbs_only_flag */
   bw_put(&b, 1, 1);             /* direct_8x8_inference_flag */
-  int crop_r = (e->cw - e->width) / 2, crop_b = (e->ch - e->height) / 2;
   if (crop_r || crop_b) { bw_put(&b, 1, 1); bw_ue(&b, 0); bw_ue(&b, crop_r); bw_ue(&b, 0); bw_ue(&b, crop_b); }
   else bw_put(&b, 1, 0);
   /* E.1.1 VUI: colour description (the CSC stage is BT.709 limited range, centre-sited chroma) and a
@@ -152,8 +159,13 @@ static void write_param_sets(enc_t* e) {
   bw_ue(&b, 0);                 /* max_num_reorder_frames */
   bw_ue(&b, 1);                 /* max_dec_frame_buffering */
   bw_trailing(&b);
-  e->sps_len = (int)nal_write(e->sps, 1, 3, 7, b.buf, b.pos);
+  int n = (int)nal_write(dst, 1, 3, 7, b.buf, b.pos);
   bw_free(&b);
+  return n;
+}
+static void write_param_sets(enc_t* e) {
+  bitw_t b;
+  e->sps_len = build_sps(e->sps, e->mbw, e->mbh, (e->cw - e->width) / 2, (e->ch - e->height) / 2);
   bw_init(&b);
   bw_ue(&b, 0); bw_ue(&b, 0);   /* pps id, sps id */
   bw_put(&b, 1, 0);             /* entropy_coding_mode_flag: CAVLC */
@@ -611,6 +623,13 @@ static void luma_mc_planes(uint8_t Gp[22][22], uint8_t bq[18][17], uint8_t hq[17
     }
 }
 
+/* macroblock rows [r0, r1) of the band (stripe) holding row mby; the whole picture when striping is off */
+static void band_rows(const enc_t* e, int mby, int* r0, int* r1) {
+  if (!e->stripe_rows) { *r0 = 0; *r1 = e->mbh; return; }
+  *r0 = mby / e->stripe_rows * e->stripe_rows;
+  *r1 = *r0 + e->stripe_rows; if (*r1 > e->mbh) *r1 = e->mbh;
+}
+
 static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
   mb_t* m = &e->mbs[mby * e->mbw + mbx];
   memset(m, 0, sizeof *m);
@@ -619,11 +638,13 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   load_cur(cur_nv12, e->cw, e->ch, mbx, mby, cy, cc);
   const uint8_t* refy = plane_y(e, e->cur ^ 1); const uint8_t* refuv = plane_uv(e, e->cur ^ 1);
   int x0 = mbx * 16, y0 = mby * 16, lambda = me_lambda[qp];
+  int br0, br1; band_rows(e, mby, &br0, &br1);
+  const int ylo = br0 * 16, yhi = br1 * 16 - 1;      /* a band's decoder pads at the band's own edges */
   uint32_t best = 0xffffffffu; int bdx = 0, bdy = 0;
   /* reference samples the search can touch, with picture-edge clamping (8.4.2.2.1): win[j][i] = ref(x0-16+i, y0-16+j) */
   uint8_t win[48][48];
   for (int j = 0; j < 48; j++) {
-    const uint8_t* rr = refy + (size_t)clip3(0, e->ch - 1, y0 - 16 + j) * e->cw;
+    const uint8_t* rr = refy + (size_t)clip3(ylo, yhi, y0 - 16 + j) * e->cw;
     if (x0 >= 16 && x0 + 32 <= e->cw) memcpy(win[j], rr + x0 - 16, 48);
     else for (int i = 0; i < 48; i++) win[j][i] = rr[clip3(0, e->cw - 1, x0 - 16 + i)];
   }
@@ -692,13 +713,13 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   /* prediction: luma from the planes above, or a full-sample copy; chroma bilinear 1/8 (8.4.2.2.2) */
   if (!have_planes)
     for (int r = 0; r < 16; r++)
-      for (int c = 0; c < 16; c++) py[r * 16 + c] = refy[(size_t)clip3(0, e->ch - 1, y0 + bdy + r) * e->cw + clip3(0, e->cw - 1, x0 + bdx + c)];
+      for (int c = 0; c < 16; c++) py[r * 16 + c] = refy[(size_t)clip3(ylo, yhi, y0 + bdy + r) * e->cw + clip3(0, e->cw - 1, x0 + bdx + c)];
   int mvcx = mvx, mvcy = mvy, xi = asr(mvcx, 3), yi = asr(mvcy, 3), xf = mvcx & 7, yf = mvcy & 7;
-  int cwc = e->cw / 2, chc = e->ch / 2;
+  int cwc = e->cw / 2;
   for (int r = 0; r < 8; r++)
     for (int c = 0; c < 8; c++) {
       int xa = clip3(0, cwc - 1, mbx * 8 + xi + c), xb = clip3(0, cwc - 1, mbx * 8 + xi + c + 1);
-      int ya = clip3(0, chc - 1, mby * 8 + yi + r), yb = clip3(0, chc - 1, mby * 8 + yi + r + 1);
+      int ya = clip3(ylo / 2, yhi / 2, mby * 8 + yi + r), yb = clip3(ylo / 2, yhi / 2, mby * 8 + yi + r + 1);
       for (int k = 0; k < 2; k++) {
         int A = refuv[(size_t)ya * e->cw + xa * 2 + k], B = refuv[(size_t)ya * e->cw + xb * 2 + k];
         int C = refuv[(size_t)yb * e->cw + xa * 2 + k], D = refuv[(size_t)yb * e->cw + xb * 2 + k];
@@ -912,11 +933,11 @@ static void write_residual(const enc_t* e, bitw_t* b, const uint8_t* skip, const
 }
 
 /* 7.3.3 slice header */
-static void write_slice_header(const enc_t* e, bitw_t* b, int first_mb, int idr, int qp) {
+static void write_slice_header(const enc_t* e, bitw_t* b, int first_mb, int idr, int qp, int frame_num) {
   bw_ue(b, first_mb);
   bw_ue(b, idr ? 7 : 5);                       /* slice_type: all slices of the picture I / P */
   bw_ue(b, 0);                                 /* pic_parameter_set_id */
-  bw_put(b, 8, e->frame_num & 255);
+  bw_put(b, 8, frame_num & 255);
   if (idr) bw_ue(b, e->idr_count & 15);        /* idr_pic_id */
   if (!idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); }   /* num_ref_idx_active_override_flag, ref_pic_list_modification_flag_l0 */
   if (idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); }    /* no_output_of_prior_pics_flag, long_term_reference_flag */
@@ -926,10 +947,12 @@ static void write_slice_header(const enc_t* e, bitw_t* b, int first_mb, int idr,
 }
 
 /* entropy-code one slice (7.3.4, 7.3.5) into a NAL appended at out; returns bytes written */
-static size_t code_slice(enc_t* e, int s, int idr, int qp, uint8_t* skip, uint8_t* out, int first_nal_of_au, int64_t* bits) {
+static size_t code_slice(enc_t* e, int s, int idr, int qp, uint8_t* skip, uint8_t* out, int64_t* bits) {
   bitw_t b; bw_init(&b);
   int row0 = s * e->slice_rows, row1 = row0 + e->slice_rows; if (row1 > e->mbh) row1 = e->mbh;
-  write_slice_header(e, &b, row0 * e->mbw, idr, qp);
+  int br0, br1; band_rows(e, row0, &br0, &br1);
+  const int first_nal_of_au = row0 == br0 && !idr;     /* 4-byte start code opens each band's access unit */
+  write_slice_header(e, &b, (row0 - br0) * e->mbw, idr, qp, idr ? 0 : e->stripe_rows ? e->stripe_fn[row0 / e->stripe_rows] : e->frame_num);
   int skip_run = 0;
   for (int mby = row0; mby < row1; mby++)
     for (int mbx = 0; mbx < e->mbw; mbx++) {
@@ -1027,7 +1050,29 @@ int b2v_ref_enc_coded_w(void* h) { return ((enc_t*)h)->cw; }
 int b2v_ref_enc_coded_h(void* h) { return ((enc_t*)h)->ch; }
 const uint8_t* b2v_ref_enc_recon(void* h) { enc_t* e = (enc_t*)h; return e->recon[e->cur]; }
 int b2v_ref_enc_last_qp(void* h) { return ((enc_t*)h)->last_qp; }
-size_t b2v_ref_enc_max_au(void* h) { enc_t* e = (enc_t*)h; return (size_t)e->mbw * e->mbh * 1024 + 4096; }
+void b2v_ref_enc_set_paintover(void* h, int trigger_frames, int qp) { enc_t* e = (enc_t*)h; e->paint_trigger = trigger_frames; e->paint_qp = qp; }
+/* striped mode: stripe_rows macroblock rows per band (a multiple of slice_rows); 0 = full frame.  Returns the band count or -1. */
+int b2v_ref_enc_set_stripes(void* h, int stripe_rows) {
+  enc_t* e = (enc_t*)h;
+  if (stripe_rows <= 0 || stripe_rows >= e->mbh) { e->stripe_rows = 0; e->n_stripes = 1; return 1; }
+  if (stripe_rows % e->slice_rows) return -1;
+  const int n = (e->mbh + stripe_rows - 1) / stripe_rows;
+  if (n > MAX_STRIPES) return -1;
+  e->stripe_rows = stripe_rows; e->n_stripes = n;
+  const int last_rows = e->mbh - (n - 1) * stripe_rows, crop_r = (e->cw - e->width) / 2;
+  e->sps_band_len[0] = build_sps(e->sps_band[0], e->mbw, stripe_rows, crop_r, 0);
+  e->sps_band_len[1] = build_sps(e->sps_band[1], e->mbw, last_rows, crop_r, (e->ch - e->height) / 2);
+  memset(e->stripe_fn, 0, sizeof e->stripe_fn);
+  return n;
+}
+/* byte offset, size and coded flag of every band of the last encoded picture (3 ints each); returns the band count */
+int b2v_ref_enc_stripe_table(void* h, int32_t* out) {
+  enc_t* e = (enc_t*)h;
+  if (!e->stripe_rows) return 0;
+  memcpy(out, e->stripe_tab, sizeof(int32_t) * 3 * e->n_stripes);
+  return e->n_stripes;
+}
+size_t b2v_ref_enc_max_au(void* h) { enc_t* e = (enc_t*)h; return (size_t)e->mbw * e->mbh * 1024 + 4096 + 128 * MAX_STRIPES; }
 
 /*
  * Encode one picture.  cur_nv12: coded_w x coded_h NV12.  rc_mode 0 = CBR (target_bits per frame,
@@ -1038,6 +1083,7 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   int mbs = e->mbw * e->mbh;
   if (rc_mode == 0 && e->rc_qp < 0) e->rc_qp = rc_initial_qp(target_bits, mbs);
   int qp = rc_mode == 1 ? clip3(0, 51, qp_fixed) : e->rc_qp;
+  if (rc_mode == 1 && e->paint_trigger > 0 && !idr && e->static_run == e->paint_trigger) qp = clip3(0, 51, e->paint_qp);
   /* CBR: an IDR requested in mid-stream (PLI, resize) is not coded finer than a fresh start with 4x the picture budget
    * would be, which bounds the latency spike of the key frame */
   if (rc_mode == 0 && idr) { int q0 = rc_initial_qp(4 * target_bits, mbs); if (qp < q0) qp = q0; }
@@ -1064,11 +1110,30 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   size_t* lens = (size_t*)calloc(e->n_slices, sizeof(size_t));
   int64_t* sbits = (int64_t*)calloc(e->n_slices, sizeof(int64_t));
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int s = 0; s < e->n_slices; s++) lens[s] = code_slice(e, s, idr, qp, skip, tmp + per * s, s == 0 && !idr, &sbits[s]);
+  for (int s = 0; s < e->n_slices; s++) lens[s] = code_slice(e, s, idr, qp, skip, tmp + per * s, &sbits[s]);
   size_t o = 0; int64_t bits = 0;
-  if (idr) { memcpy(out + o, e->sps, e->sps_len); o += e->sps_len; memcpy(out + o, e->pps, e->pps_len); o += e->pps_len; }
-  for (int s = 0; s < e->n_slices; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
-  free(skip); free(tmp); free(lens); free(sbits);
+  if (!e->stripe_rows) {
+    if (idr) { memcpy(out + o, e->sps, e->sps_len); o += e->sps_len; memcpy(out + o, e->pps, e->pps_len); o += e->pps_len; }
+    for (int s = 0; s < e->n_slices; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
+  } else {
+    /* bands back to back, each a complete access unit of its own stream; a P band whose macroblocks were all skipped
+     * is flagged not-coded (the caller drops it) and its frame_num does not advance */
+    for (int t = 0; t < e->n_stripes; t++) {
+      const int r0 = t * e->stripe_rows, r1 = r0 + e->stripe_rows > e->mbh ? e->mbh : r0 + e->stripe_rows;
+      const int last = t == e->n_stripes - 1;
+      const size_t o0 = o;
+      if (idr) { memcpy(out + o, e->sps_band[last], e->sps_band_len[last]); o += e->sps_band_len[last]; memcpy(out + o, e->pps, e->pps_len); o += e->pps_len; }
+      for (int s = r0 / e->slice_rows; s < (r1 + e->slice_rows - 1) / e->slice_rows; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
+      int coded = idr;
+      for (int i = r0 * e->mbw; i < r1 * e->mbw && !coded; i++) coded |= !skip[i];
+      e->stripe_tab[t][0] = (int32_t)o0; e->stripe_tab[t][1] = (int32_t)(o - o0); e->stripe_tab[t][2] = coded;
+      e->stripe_fn[t] = idr ? 1 : (e->stripe_fn[t] + (coded ? 1 : 0)) & 255;
+    }
+  }
+  uint8_t* skip_copy = skip;
+  free(tmp); free(lens); free(sbits);
+  { int coded = 0; for (int i = 0; i < mbs; i++) coded |= !skip_copy[i]; int painted = rc_mode == 1 && e->paint_trigger > 0 && !idr && e->static_run == e->paint_trigger;
+    e->static_run = painted ? e->paint_trigger + 1 : (coded || idr) ? 0 : e->static_run + 1; free(skip_copy); }
   e->last_qp = qp; e->last_bits = (int64_t)o * 8;
   if (rc_mode == 0) rc_update(e, (int64_t)o * 8, target_bits, idr);
   if (idr) e->idr_count++;

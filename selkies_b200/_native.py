@@ -25,7 +25,7 @@ class B2VSettings(C.Structure):
         ("fps", C.c_double), ("device", C.c_int32), ("rc_mode", C.c_int32),
         ("bitrate_kbps", C.c_int32), ("crf", C.c_int32), ("gop", C.c_int32),
         ("slice_rows", C.c_int32), ("header_mode", C.c_int32), ("ring_slots", C.c_int32),
-        ("flags", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("flags", C.c_int32), ("paintover_trigger_frames", C.c_int32), ("paintover_crf", C.c_int32), ("stripe_rows", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -33,6 +33,7 @@ class B2VFrame(C.Structure):
     _fields_ = [
         ("data", C.POINTER(C.c_ubyte)), ("size", C.c_int32), ("frame_id", C.c_int32),
         ("is_key", C.c_int32), ("qp", C.c_int32), ("pts90k", C.c_int64), ("capture_ns", C.c_int64),
+        ("y_start", C.c_int32), ("height", C.c_int32),
     ]
 
 
@@ -111,7 +112,7 @@ def lib():
                 fn = getattr(l, name)          # AttributeError here = header/library mismatch
                 fn.restype = res
                 fn.argtypes = args
-            if l.b2v_abi_version() != 1:
+            if l.b2v_abi_version() != 2:
                 raise ImportError("libb2video ABI version mismatch")
             _lib = l
     return _lib

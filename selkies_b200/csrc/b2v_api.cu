@@ -74,6 +74,7 @@ struct Session {
   cudaEvent_t ev_enc[kMaxSlots] = {}, ev_out[kMaxSlots] = {};
   bool out_free[kMaxSlots] = {};
   size_t au_cap = 0;
+  int au_data_off = 64, n_bands = 0;   // bytes in front of the first NAL in d_au (AuHeader [+ band table]); bands when striped
   int out_next = 0;
   int ring_next = 0;
   cudaEvent_t ev_timer[2] = {};
@@ -129,9 +130,12 @@ int alloc_geometry(Session* s) {
     ec.width = s->dst_w; ec.height = s->dst_h; ec.coded_w = s->coded_w; ec.coded_h = s->coded_h;
     ec.slice_rows = s->cfg.slice_rows > 0 ? s->cfg.slice_rows : 1;
     ec.sm_count = s->sm_count;
+    ec.stripe_rows = s->cfg.stripe_rows > 0 ? s->cfg.stripe_rows : 0;
     int rc = encoder_create(&ec, &s->enc);
     if (rc) return fail(rc, "encoder_create failed: %s", encoder_last_error());
     s->au_cap = encoder_au_capacity(s->enc);
+    s->au_data_off = encoder_au_data_offset(s->enc);
+    s->n_bands = encoder_band_count(s->enc);
     for (int i = 0; i < s->n_slots; i++) {
       CK(cudaMalloc((void**)&s->d_au[i], s->au_cap));
       CK(cudaHostAlloc((void**)&s->h_out[i], s->au_cap + kOutHead, cudaHostAllocDefault));
@@ -184,7 +188,8 @@ void output_loop(Session* s) {
       uint8_t* base = s->h_out[j.out_idx];
       const AuHeader* ah = (const AuHeader*)base;     // device wrote the AU header at the start of the buffer
       size = ah->size; qp = ah->qp;
-      if (se != cudaSuccess || size < 0 || (size_t)size + sizeof(AuHeader) > s->au_cap || ah->overflow) {
+      const size_t doff = (size_t)s->au_data_off;
+      if (se != cudaSuccess || size < 0 || (size_t)size + doff > s->au_cap || ah->overflow) {
         // a kernel faulted or produced an impossible access unit: fail loudly — nothing is delivered, every later
         // call on this session returns B2V_ECUDA with this message
         std::lock_guard<std::mutex> lk(s->mu);
@@ -193,16 +198,16 @@ void output_loop(Session* s) {
         s->failed = true;
         size = 0;
       }
-      if ((size_t)size + sizeof(AuHeader) > kFirstChunk && size > 0) {   // oversized AU: fetch the tail
+      if ((size_t)size + doff > kFirstChunk && size > 0) {   // oversized AU: fetch the tail
         size_t have = kFirstChunk;
-        cudaMemcpyAsync(base + have, s->d_au[j.out_idx] + have, sizeof(AuHeader) + (size_t)size - have, cudaMemcpyDeviceToHost, s->st_out);
+        cudaMemcpyAsync(base + have, s->d_au[j.out_idx] + have, doff + (size_t)size - have, cudaMemcpyDeviceToHost, s->st_out);
         cudaStreamSynchronize(s->st_out);
         std::lock_guard<std::mutex> lk(s->mu);
-        s->stats.d2h_bytes += (int64_t)(sizeof(AuHeader) + size - have);
+        s->stats.d2h_bytes += (int64_t)(doff + size - have);
       }
-      uint8_t* au = base + sizeof(AuHeader);
+      uint8_t* au = base + doff;
       data = au;
-      if (s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
+      if (s->n_bands == 0 && s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
         // 10-byte stripe header written into the slack in front of the AU (AuHeader is 64 bytes; already consumed)
         uint8_t* h = au - 10;
         h[0] = 0x04; h[1] = j.is_key ? 1 : 0;
@@ -238,10 +243,39 @@ void output_loop(Session* s) {
       }
       s->stats.ms_total_gpu += ms[5];
     }
-    if (s->cb && s->encode && size > 0) {
+    if (s->encode && size > 0 && s->n_bands > 0) {
+      // striped mode: one callback per band that carries data, in picture order.  The band table is copied out first:
+      // the 10-byte header of band k is written over the tail of band k-1 (already delivered) or the table slack.
+      std::vector<BandEntry> tab(s->n_bands);
+      memcpy(tab.data(), s->h_out[j.out_idx] + sizeof(AuHeader), sizeof(BandEntry) * s->n_bands);
+      uint8_t* au = s->h_out[j.out_idx] + s->au_data_off;
+      const int rows = s->cfg.stripe_rows * 16;
+      int delivered_bytes = 0;
+      for (int b = 0; b < s->n_bands; b++) {
+        const BandEntry& be = tab[b];
+        if (!be.coded || be.size <= 0 || (long long)be.off + be.size > size) continue;
+        const int y0 = b * rows, bh = (y0 + rows <= j.hdr_h) ? rows : j.hdr_h - y0;
+        b2v_frame f{};
+        f.data = au + be.off; f.size = be.size;
+        if (s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
+          uint8_t* h = au + be.off - 10;
+          h[0] = 0x04; h[1] = j.is_key ? 1 : 0;
+          h[2] = (uint8_t)(j.frame_id >> 8); h[3] = (uint8_t)j.frame_id;
+          h[4] = (uint8_t)(y0 >> 8); h[5] = (uint8_t)y0;
+          h[6] = (uint8_t)(j.hdr_w >> 8); h[7] = (uint8_t)j.hdr_w;
+          h[8] = (uint8_t)(bh >> 8); h[9] = (uint8_t)bh;
+          f.data = h; f.size += 10;
+        }
+        f.frame_id = j.frame_id; f.is_key = j.is_key; f.qp = qp; f.pts90k = j.pts; f.capture_ns = j.capture_ns;
+        f.y_start = y0; f.height = bh;
+        delivered_bytes += f.size;
+        if (s->cb) s->cb(&f, s->user);
+      }
+      size = delivered_bytes;
+    } else if (s->cb && s->encode && size > 0) {
       b2v_frame f{};
       f.data = data; f.size = size; f.frame_id = j.frame_id; f.is_key = j.is_key; f.qp = qp;
-      f.pts90k = j.pts; f.capture_ns = j.capture_ns;
+      f.pts90k = j.pts; f.capture_ns = j.capture_ns; f.y_start = 0; f.height = j.hdr_h;
       s->cb(&f, s->user);
     }
     {
@@ -283,6 +317,8 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
     fp.idr = idr;
     fp.rc_mode = s->cfg.rc_mode;
     fp.qp_fixed = s->qp_fixed;
+    fp.paint_trigger = s->cfg.paintover_trigger_frames > 0 ? s->cfg.paintover_trigger_frames : 0;
+    fp.paint_qp = s->cfg.paintover_crf;
     // target bits per frame for the device-side rate controller
     fp.target_bits = (int64_t)((double)s->bitrate_kbps * 1000.0 / (s->fps > 0 ? s->fps : 60.0));
     s->submitted++;

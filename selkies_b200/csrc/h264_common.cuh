@@ -30,11 +30,14 @@ struct RcState {
   long long fullness;
   int32_t last_qp;
   int32_t frames;
+  int32_t static_run;      // consecutive pictures in which every macroblock was skipped
+  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by the pack kernel
 };
 
 struct FrameCtx {          // everything a kernel needs about the picture being coded
   int cw, ch, mbw, mbh, slice_rows, n_slices;
   int idr, rc_mode, qp_fixed;
+  int paint_trigger, paint_qp;   // CQP mode paint-over: one refinement picture after `paint_trigger` all-skipped pictures (0 = off)
   long long target_bits;
   int frame_num, idr_pic_id;
   const uint8_t* cur;      // NV12 coded size
@@ -56,6 +59,13 @@ struct FrameCtx {          // everything a kernel needs about the picture being 
   int* progress;           // [mbh] intra wavefront progress counters
   RcState* rc;
   const uint8_t* param_sets; int param_len;   // SPS+PPS NAL bytes (IDR pictures)
+  // bands ("stripes", pixelflux h264_fullframe = False): groups of band_rows macroblock rows, each an independent H.264
+  // stream.  Full-frame coding is the one-band case (band_rows = mbh, striped = 0).
+  int band_rows, n_bands, striped;
+  int param_len_last;      // SPS+PPS of the last band (may be shorter / cropped), stored behind the regular set
+  int* band_fn;            // [n_bands] frame_num of each band's next picture (advances only when the band is coded)
+  int* band_coded;         // [n_bands] set by the slice scan when a band holds a non-skipped macroblock; cleared by the pack kernel
+  int au_data_off;         // bytes from the AuHeader to the first NAL (AuHeader + band table)
   const unsigned long long* csc_ts;            // device stamps of this picture's CSC launch (or null)
   uint8_t* au;             // AuHeader + access unit
   int* overflow;
@@ -69,7 +79,11 @@ __device__ __forceinline__ int rc_initial_qp(long long target_bits, int mbs) {
   return per_mb >= 400 ? 22 : per_mb >= 200 ? 26 : per_mb >= 100 ? 30 : per_mb >= 50 ? 34 : per_mb >= 25 ? 38 : 42;
 }
 __device__ __forceinline__ int frame_qp(const FrameCtx& f) {
-  if (f.rc_mode == 1) return clip3i(0, 51, f.qp_fixed);
+  if (f.rc_mode == 1) {
+    // paint-over: the scene has been static for `paint_trigger` pictures -> one picture at the (finer) paint-over QP
+    if (f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger) return clip3i(0, 51, f.paint_qp);
+    return clip3i(0, 51, f.qp_fixed);
+  }
   int q = f.rc->qp;
   if (q < 0) q = rc_initial_qp(f.target_bits, f.mbw * f.mbh);
   // an IDR in mid-stream is not coded finer than a fresh start with 4x the picture budget would be (bounds the key-frame burst)

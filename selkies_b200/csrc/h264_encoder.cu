@@ -33,7 +33,9 @@ struct Encoder {
   int* progress = nullptr;
   int* overflow = nullptr;
   RcState* rc = nullptr;
-  uint8_t* param_sets = nullptr; int param_len = 0;
+  uint8_t* param_sets = nullptr; int param_len = 0, param_len_last = 0;
+  int band_rows = 0, n_bands = 1, striped = 0, au_data_off = (int)sizeof(AuHeader);
+  int *band_fn = nullptr, *band_coded = nullptr;
   size_t au_cap = 0;
   int frame_num = 0, idr_count = 0;
   bool have_ref = false;
@@ -67,7 +69,7 @@ void append_nal(std::vector<uint8_t>& out, int ref_idc, int type, const std::vec
 
 int level_idc_for(int mbs) { return mbs <= 3600 ? 31 : mbs <= 8704 ? 42 : mbs <= 22080 ? 51 : mbs <= 36864 ? 52 : 62; }
 
-std::vector<uint8_t> make_param_sets(const EncoderConfig& c, int mbw, int mbh) {
+std::vector<uint8_t> make_param_sets(const EncoderConfig& c, int mbw, int mbh, int crop_b) {
   std::vector<uint8_t> out;
   HostBits b;
   b.put(8, 66); b.put(8, 0xC0); b.put(8, (uint32_t)level_idc_for(mbw * mbh));
@@ -79,7 +81,7 @@ std::vector<uint8_t> make_param_sets(const EncoderConfig& c, int mbw, int mbh) {
   b.ue(mbw - 1); b.ue(mbh - 1);
   b.put(1, 1);             // frame_mbs_only_flag
   b.put(1, 1);             // direct_8x8_inference_flag
-  const int crop_r = (c.coded_w - c.width) / 2, crop_b = (c.coded_h - c.height) / 2;
+  const int crop_r = (c.coded_w - c.width) / 2;
   if (crop_r || crop_b) { b.put(1, 1); b.ue(0); b.ue(crop_r); b.ue(0); b.ue(crop_b); } else b.put(1, 0);
   // E.1.1 VUI: BT.709 limited-range colour description, centre-sited chroma, no picture reordering
   b.put(1, 1);             // vui_parameters_present_flag
@@ -156,11 +158,27 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMalloc((void**)&e->rc, sizeof(RcState)));
   RcState rc0{}; rc0.qp = -1;
   ECK(cudaMemcpy(e->rc, &rc0, sizeof rc0, cudaMemcpyHostToDevice));
-  std::vector<uint8_t> ps = make_param_sets(*cfg, e->mbw, e->mbh);
+  // bands: full-frame coding is one band of mbh rows; striped mode gives every band its own SPS (height = the band's)
+  const int crop_b = (cfg->coded_h - cfg->height) / 2;
+  e->striped = cfg->stripe_rows > 0 && cfg->stripe_rows < e->mbh;
+  if (e->striped && cfg->stripe_rows % cfg->slice_rows) { snprintf(g_enc_err, sizeof g_enc_err, "stripe_rows must be a multiple of slice_rows"); encoder_destroy(e); return -1; }
+  e->band_rows = e->striped ? cfg->stripe_rows : e->mbh;
+  e->n_bands = (e->mbh + e->band_rows - 1) / e->band_rows;
+  std::vector<uint8_t> ps = make_param_sets(*cfg, e->mbw, e->band_rows, e->striped ? 0 : crop_b);
   e->param_len = (int)ps.size();
+  if (e->striped) {
+    std::vector<uint8_t> last = make_param_sets(*cfg, e->mbw, e->mbh - (e->n_bands - 1) * e->band_rows, crop_b);
+    e->param_len_last = (int)last.size();
+    ps.insert(ps.end(), last.begin(), last.end());
+    e->au_data_off = (int)sizeof(AuHeader) + ((e->n_bands * (int)sizeof(BandEntry) + 16 + 63) & ~63);
+  }
   ECK(cudaMalloc((void**)&e->param_sets, ps.size()));
   ECK(cudaMemcpy(e->param_sets, ps.data(), ps.size(), cudaMemcpyHostToDevice));
-  e->au_cap = sizeof(AuHeader) + ps.size() + (size_t)e->n_slices * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
+  ECK(cudaMalloc((void**)&e->band_fn, e->n_bands * sizeof(int)));
+  ECK(cudaMemset(e->band_fn, 0, e->n_bands * sizeof(int)));
+  ECK(cudaMalloc((void**)&e->band_coded, e->n_bands * sizeof(int)));
+  ECK(cudaMemset(e->band_coded, 0, e->n_bands * sizeof(int)));
+  e->au_cap = (size_t)e->au_data_off + (size_t)e->n_bands * (e->param_len + e->param_len_last) + (size_t)e->n_slices * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
   *out = e;
   return 0;
 }
@@ -168,12 +186,14 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
 void encoder_destroy(Encoder* e) {
   if (!e) return;
   void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo, e->coef, e->nnz, e->mb_words, e->mb_nbits, e->slice_buf, e->slice_size,
-                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes};
+                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes, e->band_fn, e->band_coded};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete e;
 }
 
 size_t encoder_au_capacity(const Encoder* e) { return e->au_cap; }
+int encoder_au_data_offset(const Encoder* e) { return e->au_data_off; }
+int encoder_band_count(const Encoder* e) { return e->striped ? e->n_bands : 0; }
 const uint8_t* encoder_recon(const Encoder* e) { return e->recon[e->cur]; }
 
 int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
@@ -188,7 +208,9 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
   f.mbinfo = e->mbinfo; f.i4modes = e->i4modes; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
   f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
-  f.slice_bits = e->slice_bits; f.progress = e->progress; f.rc = e->rc;
+  f.slice_bits = e->slice_bits; f.paint_trigger = p->paint_trigger; f.paint_qp = p->paint_qp; f.progress = e->progress; f.rc = e->rc;
+  f.band_rows = e->band_rows; f.n_bands = e->n_bands; f.striped = e->striped; f.param_len_last = e->param_len_last;
+  f.band_fn = e->band_fn; f.band_coded = e->band_coded; f.au_data_off = e->au_data_off;
   f.param_sets = e->param_sets; f.param_len = e->param_len; f.csc_ts = p->csc_ts; f.au = p->au; f.overflow = e->overflow;
   int n = 0;
   n += idr ? launch_intra(f, st) : launch_inter(f, st);

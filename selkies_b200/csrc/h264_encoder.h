@@ -13,6 +13,7 @@ struct EncoderConfig {
   int width, height;       // visible size (SPS cropping)
   int coded_w, coded_h;    // multiples of 16
   int slice_rows;          // macroblock rows per slice
+  int stripe_rows;         // macroblock rows per band (multiple of slice_rows); 0 = full-frame
   int sm_count;
 };
 
@@ -31,12 +32,16 @@ struct AuHeader {
 };
 static_assert(sizeof(AuHeader) == 64, "AuHeader must be 64 bytes");
 
+// striped mode: one record per band right after the AuHeader (offsets relative to the first NAL byte)
+struct BandEntry { int32_t off, size, coded, frame_num; };
+
 struct EncodeFrameParams {
   const uint8_t* cur;      // NV12, coded size, device
   uint8_t* au;             // device buffer, encoder_au_capacity() bytes; AuHeader first
   int idr;
   int rc_mode;             // B2V_RC_CBR | B2V_RC_CQP
   int qp_fixed;
+  int paint_trigger, paint_qp;   // CQP paint-over (0 = off)
   int64_t target_bits;     // per frame, CBR
   cudaEvent_t* ev;         // null, or 8 timing events: encoder records ev[2..5] after each stage
   const unsigned long long* csc_ts;   // null, or the CSC launch's device stamps to forward in the AuHeader
@@ -45,6 +50,8 @@ struct EncodeFrameParams {
 int  encoder_create(const EncoderConfig* cfg, Encoder** out);
 void encoder_destroy(Encoder* e);
 size_t encoder_au_capacity(const Encoder* e);
+int  encoder_au_data_offset(const Encoder* e);   // AuHeader + band table (+ slack for an in-place stripe header)
+int  encoder_band_count(const Encoder* e);       // 0 when full-frame
 // enqueue one frame on `st`; returns the number of kernel launches issued
 int  encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st);
 const uint8_t* encoder_recon(const Encoder* e);   // NV12 reconstruction of the last encoded frame

@@ -193,11 +193,11 @@ __global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
 
 // ------------------------------------------------------------------------------------------------ slice header (7.3.3)
 template <class S>
-__device__ __forceinline__ void slice_header(S& s, const FrameCtx& f, int first_mb, int qp) {
+__device__ __forceinline__ void slice_header(S& s, const FrameCtx& f, int first_mb, int qp, int frame_num) {
   put_ue(s, (uint32_t)first_mb);
   put_ue(s, f.idr ? 7u : 5u);
   put_ue(s, 0);
-  s.put(8, (uint32_t)(f.frame_num & 255));
+  s.put(8, (uint32_t)(frame_num & 255));
   if (f.idr) put_ue(s, (uint32_t)(f.idr_pic_id & 15));
   if (!f.idr) { s.put(1, 0); s.put(1, 0); }
   if (f.idr) { s.put(1, 0); s.put(1, 0); } else s.put(1, 0);
@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
   uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
   if (tid == 0) {
     GlobalSink g{out, 0};
-    slice_header(g, f, mb0, qp);
+    const int band = row0 / f.band_rows;      // first_mb_in_slice and frame_num are the band's own
+    slice_header(g, f, mb0 - band * f.band_rows * f.mbw, qp, f.idr ? 0 : f.striped ? f.band_fn[band] : f.frame_num);
     s_carry_bits = g.pos; s_carry_last = -1;
   }
   __syncthreads();
@@ -311,6 +312,10 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
     GlobalSink g{out, s_carry_bits};
     if (!f.idr) { const int run = n_mb - 1 - s_carry_last; if (run > 0) put_ue(g, (uint32_t)run); }
     f.slice_bits[s] = g.pos;
+    if (s_carry_last >= 0) {                          // benign races: every writer stores the same value
+      f.rc->pic_coded = 1;
+      if (f.striped) f.band_coded[row0 / f.band_rows] = 1;
+    }
     g.put(1, 1);
     f.slice_rbsp[s] = (uint32_t)((g.pos + 7) >> 3);
   }
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_ep(FrameCtx f) {
   if (tid == 0) {
     int t = 0;
     for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_red[w];
-    const int start_len = (s == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of the access unit
+    const int start_len = ((s * f.slice_rows) % f.band_rows == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of (each band's) access unit
     f.slice_size[s] = (uint32_t)(start_len + 1 + rbsp_bytes + t);
   }
 }
@@ -420,18 +425,21 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
   __shared__ long long s_part[PACK_THREADS / 32];
   if (lane == 0) s_part[warp] = part;
   __syncthreads();
+  const int row0 = s * f.slice_rows, band = row0 / f.band_rows;
+  const bool band_first = row0 == band * f.band_rows;                     // this slice opens its band's access unit
+  const int plen = (f.striped && band == f.n_bands - 1) ? f.param_len_last : f.param_len;
   if (tid == 0) {
-    long long t = f.idr ? f.param_len : 0;
+    long long t = f.idr ? (long long)band * f.param_len + plen : 0;       // parameter sets of bands 0..band precede this NAL
     for (int w = 0; w < PACK_THREADS / 32; w++) t += s_part[w];
     s_base = t; s_carry = 0;
   }
   __syncthreads();
-  uint8_t* au = f.au + sizeof(AuHeader);
-  const long long cap = au_cap - (long long)sizeof(AuHeader);
+  uint8_t* au = f.au + f.au_data_off;
+  const long long cap = au_cap - (long long)f.au_data_off;
   const long long base = s_base;
   const uint32_t* in = f.slice_buf + (size_t)s * f.slice_words;
   const long long n = f.slice_rbsp[s];
-  const int start_len = (s == 0 && !f.idr) ? 4 : 3;
+  const int start_len = (band_first && !f.idr) ? 4 : 3;
   if (tid == 0 && base + start_len + 1 <= cap) {
     long long o = base;
     if (start_len == 4) au[o++] = 0;
@@ -483,10 +491,26 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
     const long long nw = min((long long)f.slice_words, (n >> 2) + 2);
     for (long long i = tid; i < nw; i += PACK_THREADS) w[i] = 0;
   }
+  if (band_first) {
+    if (f.idr && base <= cap) {
+      const uint8_t* ps = f.param_sets + ((f.striped && band == f.n_bands - 1) ? f.param_len : 0);
+      for (int i = tid; i < plen; i += PACK_THREADS) au[base - plen + i] = ps[i];
+    }
+    if (f.striped && tid == 0) {      // band table entry; the band's frame_num advances only if it is delivered
+      long long sz = f.idr ? plen : 0;
+      const int s1 = min(f.n_slices, (min(f.mbh, (band + 1) * f.band_rows) + f.slice_rows - 1) / f.slice_rows);
+      for (int j = s; j < s1; j++) sz += f.slice_size[j];
+      const int coded = f.idr ? 1 : f.band_coded[band];
+      const int fn = f.idr ? 0 : f.band_fn[band];
+      BandEntry* be = reinterpret_cast<BandEntry*>(f.au + sizeof(AuHeader)) + band;
+      be->off = (int32_t)(base - (f.idr ? plen : 0)); be->size = (int32_t)sz; be->coded = coded; be->frame_num = fn;
+      f.band_fn[band] = (fn + (coded ? 1 : 0)) & 255;
+      f.band_coded[band] = 0;
+    }
+  }
   if (s == 0) {
-    if (f.idr) for (int i = tid; i < f.param_len; i += PACK_THREADS) au[i] = f.param_sets[i];
     if (tid == 0) {
-      long long total = f.idr ? f.param_len : 0, bits = 0;
+      long long total = f.idr ? (long long)(f.n_bands - 1) * f.param_len + (f.striped ? f.param_len_last : f.param_len) : 0, bits = 0;
       for (int j = 0; j < f.n_slices; j++) { total += f.slice_size[j]; bits += f.slice_bits[j]; }
       AuHeader* h = reinterpret_cast<AuHeader*>(f.au);
       int ovf = *f.overflow;
@@ -499,6 +523,11 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
       h->next_qp = f.rc->qp;
       h->csc_t0 = f.csc_ts ? f.csc_ts[0] : 0; h->csc_t1 = f.csc_ts ? f.csc_ts[1] : 0;
       f.rc->last_qp = qp; f.rc->frames++;
+      const int coded = f.rc->pic_coded;
+      f.rc->pic_coded = 0;
+      // a paint-over picture parks the counter above the trigger, so the scene is refined once until something moves again
+      const bool painted = f.rc_mode == 1 && f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger;
+      f.rc->static_run = painted ? f.paint_trigger + 1 : (coded || f.idr) ? 0 : f.rc->static_run + 1;
     }
   }
 }

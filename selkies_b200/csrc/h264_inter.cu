@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   MbTile& t = sm.t;
   const int mbx = mb % f.mbw, mby = mb / f.mbw, x0 = mbx * 16, y0 = mby * 16;
   const int qp = frame_qp(f);
+  // reference rows this macroblock may touch: its own band (the band's decoder pads at the band's edges, 8.4.2.2.1)
+  const int band_r0 = mby / f.band_rows * f.band_rows;
+  const int ylo = band_r0 * 16, yhi = min(f.mbh, band_r0 + f.band_rows) * 16 - 1;
   const size_t ysz = (size_t)f.cw * f.ch;
   const uint8_t* __restrict__ ref_y = f.ref; const uint8_t* __restrict__ ref_uv = f.ref + ysz;
   const int r8 = lane >> 1, c8 = (lane & 1) * 8, rc4 = lane >> 2, cc4 = (lane & 3) * 4;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
 #pragma unroll
       for (int k = 0; k < 18; k++) {
         const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        v[k] = __ldg(base + (size_t)clip3i(0, f.ch - 1, y0 - 16 + row) * (f.cw >> 2) + w);
+        v[k] = __ldg(base + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * (f.cw >> 2) + w);
       }
 #pragma unroll
       for (int k = 0; k < 18; k++) {
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     } else {   // picture edge: per-sample clamping (8.4.2.2.1 reference sample padding)
       for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
         const int row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        const uint8_t* rr = ref_y + (size_t)clip3i(0, f.ch - 1, y0 - 16 + row) * f.cw;
+        const uint8_t* rr = ref_y + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * f.cw;
         uint32_t v = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rr + clip3i(0, f.cw - 1, x0 - 16 + w * 4 + k)) << (8 * k);
@@ -264,8 +267,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     }
     // chroma: mvC = luma mv, in 1/8 chroma samples (8.4.1.4, 8.4.2.2.2)
     const int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
-    const int cwc = f.cw >> 1, chc = f.ch >> 1;
-    const int ya = clip3i(0, chc - 1, mby * 8 + yi + rc4), yb = clip3i(0, chc - 1, mby * 8 + yi + rc4 + 1);
+    const int cwc = f.cw >> 1;
+    const int ya = clip3i(ylo >> 1, yhi >> 1, mby * 8 + yi + rc4), yb = clip3i(ylo >> 1, yhi >> 1, mby * 8 + yi + rc4 + 1);
     uint32_t out = 0;
 #pragma unroll
     for (int px = 0; px < 2; px++) {

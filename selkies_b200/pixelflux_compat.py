@@ -68,6 +68,7 @@ class CaptureSettings:
         self.gpu_id = 0                          # settings.py:162 exists but is never forwarded
         self.keyframe_distance = -1              # settings.py:163
         self.slice_rows = 0
+        self.h264_stripe_rows = 0                # striped mode (h264_fullframe False): macroblock rows per stripe; 0 = about 8 stripes
         self.output_width = 0                    # != capture size => fused bilinear scale
         self.output_height = 0
 
@@ -212,6 +213,17 @@ class ScreenCapture:
             s.header_mode = N.B2V_HDR_PIXELFLUX       # callers strip / keep the 10-byte header themselves
             s.ring_slots = 4
             s.flags = 0
+            if bool(getattr(settings, "use_paint_over_quality", False)) and not bool(settings.h264_cbr_mode):
+                s.paintover_trigger_frames = int(getattr(settings, "paint_over_trigger_frames", 15) or 0)
+                s.paintover_crf = int(getattr(settings, "h264_paintover_crf", 18))
+            if not bool(getattr(settings, "h264_fullframe", True)):
+                # "x264enc-striped" (selkies.py:3219): independent H.264 stripes, unchanged stripes are not sent
+                sl = max(1, s.slice_rows)
+                rows = int(getattr(settings, "h264_stripe_rows", 0) or 0)
+                if rows <= 0:
+                    mbh = ((int(s.dst_h) or h) + 15) // 16
+                    rows = -(-mbh // 8)
+                s.stripe_rows = -(-rows // sl) * sl
             self._user_cb = callback
             self._cb_native = N.FRAME_CB(self._on_frame)
             handle = C.c_void_p()

@@ -16,21 +16,22 @@ from . import _native as N
 
 
 class EncodedFrame:
-    __slots__ = ("data", "frame_id", "is_key", "qp", "pts90k", "capture_ns")
+    __slots__ = ("data", "frame_id", "is_key", "qp", "pts90k", "capture_ns", "y_start", "height")
 
-    def __init__(self, data: bytes, frame_id: int, is_key: bool, qp: int, pts90k: int, capture_ns: int):
+    def __init__(self, data: bytes, frame_id: int, is_key: bool, qp: int, pts90k: int, capture_ns: int, y_start: int = 0, height: int = 0):
         self.data = data
         self.frame_id = frame_id
         self.is_key = is_key
         self.qp = qp
         self.pts90k = pts90k
         self.capture_ns = capture_ns
+        self.y_start, self.height = y_start, height
 
 
 class Session:
     def __init__(self, width: int, height: int, *, dst_width: int = 0, dst_height: int = 0, fps: float = 60.0,
                  device: int = 0, rc_mode: int = N.B2V_RC_CBR, bitrate_kbps: int = 8000, crf: int = 26,
-                 gop: int = -1, slice_rows: int = 0, header_mode: int = N.B2V_HDR_NONE, ring_slots: int = 4,
+                 gop: int = -1, slice_rows: int = 0, paintover_trigger_frames: int = 0, paintover_crf: int = 18, stripe_rows: int = 0, header_mode: int = N.B2V_HDR_NONE, ring_slots: int = 4,
                  flags: int = 0, on_frame: Optional[Callable[[C.POINTER(N.B2VFrame)], None]] = None,
                  collect: bool = True):
         self._lib = N.lib()
@@ -44,6 +45,7 @@ class Session:
         s.src_w, s.src_h, s.dst_w, s.dst_h = width, height, dst_width, dst_height
         s.fps, s.device, s.rc_mode, s.bitrate_kbps, s.crf = float(fps), device, rc_mode, bitrate_kbps, crf
         s.gop, s.slice_rows, s.header_mode, s.ring_slots, s.flags = gop, slice_rows, header_mode, ring_slots, flags
+        s.paintover_trigger_frames, s.paintover_crf, s.stripe_rows = paintover_trigger_frames, paintover_crf, stripe_rows
         self._cb = N.FRAME_CB(self._callback)        # keep alive for the lifetime of the handle
         h = C.c_void_p()
         N.check(self._lib.b2v_create(C.byref(s), self._cb, None, C.byref(h)))
@@ -55,7 +57,7 @@ class Session:
             self._on_frame(fptr)
         if self._collect:
             f = fptr.contents
-            rec = EncodedFrame(C.string_at(f.data, f.size), f.frame_id, bool(f.is_key), f.qp, f.pts90k, f.capture_ns)
+            rec = EncodedFrame(C.string_at(f.data, f.size), f.frame_id, bool(f.is_key), f.qp, f.pts90k, f.capture_ns, f.y_start, f.height)
             with self._lock:
                 self.frames.append(rec)
 

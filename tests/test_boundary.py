@@ -26,13 +26,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/b2video.h but not exported"
     bound = {n for n, _, _ in _native.SYMBOLS}
     assert set(declared) == bound, set(declared) ^ bound
-    assert _native.lib().b2v_abi_version() == 1          # no compute call: safe without a GPU
+    assert _native.lib().b2v_abi_version() == 2          # no compute call: safe without a GPU
 
 
 def test_struct_layouts_match_header():
     from selkies_b200 import _native as N
     assert ctypes.sizeof(N.B2VSettings) == 4 * 4 + 8 + 9 * 4 + 4 * 4 + 4    # padded to 8
-    assert ctypes.sizeof(N.B2VFrame) == 8 + 4 * 4 + 8 + 8
+    assert ctypes.sizeof(N.B2VFrame) == 8 + 4 * 4 + 8 + 8 + 2 * 4 and N.B2VFrame.y_start.offset == 40
     assert N.B2VSettings.fps.offset == 16 and N.B2VSettings.device.offset == 24
 
 

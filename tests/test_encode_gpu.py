@@ -214,3 +214,29 @@ def test_8k_encode_decodes_to_its_reconstruction():
     for (Y, U, V), (ry, ruv) in zip(dec, recs):
         assert np.array_equal(Y, ry[:h, :w]) and np.array_equal(U, ruv[: h // 2, 0:w:2]) and np.array_equal(V, ruv[: h // 2, 1:w:2])
     assert len(got[1].data) < len(got[0].data) // 3          # the translation was found
+
+
+def test_paintover_bit_exact():
+    """CQP paint-over (CaptureSettings.use_paint_over_quality, selkies.py:3226-3229): after `trigger` all-skipped pictures one
+    picture is coded at the paint-over QP, once, until the scene moves again."""
+    w, h = 320, 192
+    a, b = natural_frames(w, h)[0], synth.desktop(w, h, 2)
+    frames = [a] * 7 + [b] * 11
+    enc = oracle.RefEncoder(w, h, 1)
+    enc.set_paintover(3, 16)
+    ref = [enc.encode_bgra(f, i == 0, rc_mode=1, qp=32, target_bits=0) for i, f in enumerate(frames)]
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=32, slice_rows=1, paintover_trigger_frames=3, paintover_crf=16) as s:
+        for f in frames:
+            s.submit(f)
+        s.flush()
+        got = s.take_frames()
+        grec = s.recon()
+    assert_same(got, ref, grec, enc.recon())
+    qps = [g.qp for g in got]
+    painted = [i for i, q in enumerate(qps) if q == 16]
+    assert len(painted) == 2 and painted[0] in (4, 5) and painted[1] >= 10 and painted[1] < 17 and set(qps) == {16, 32}
+    k = painted[0]
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    sy, _ = oracle.csc_nv12(a)
+    assert avdec.psnr(dec[k][0], sy) > avdec.psnr(dec[k - 1][0], sy) + 4.0  # the static text got sharper
+    assert len(got[k + 1].data) < 150                                        # and is skipped again afterwards
