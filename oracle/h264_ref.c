@@ -587,6 +587,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
 
 /* ------------------------------------------------------------------ inter macroblock (8.4) */
 #define ME_EARLY_SAD_PER_LAMBDA 96
+#define ME_PRED_SAD_FACTOR 4
 #define ME_FRAC_PENALTY_BITS 4   /* fractional vectors pay 4 extra bits: they cost more mvd bits than the zero-relative estimate sees */
 static int se_bits(int v) { unsigned c = v > 0 ? 2u * v - 1 : (unsigned)(-2 * v); int len = 0; c += 1; while ((c >> len) > 1) len++; return 2 * len + 1; }
 
@@ -632,6 +633,7 @@ static void band_rows(const enc_t* e, int mby, int* r0, int* r1) {
 
 static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
   mb_t* m = &e->mbs[mby * e->mbw + mbx];
+  const int prev_type = m->type, prev_mvx = m->mv[0], prev_mvy = m->mv[1];   /* this macroblock in the previous picture */
   memset(m, 0, sizeof *m);
   m->type = 1;
   uint8_t cy[256], cc[2][64];
@@ -652,7 +654,30 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
    * expected at this QP (SAD <= 96*lambda), the search is skipped and mv = (0,0) */
   int sad0 = 0;
   for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) sad0 += iabs(cy[r * 16 + c] - win[16 + r][16 + c]);
-  const int search = sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda;
+  int search = sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda;
+  /* temporal-predictor early termination: the vector this macroblock had in the previous picture, rounded to full samples
+   * (scrolling and panning content repeats it).  Accepted without the exhaustive search when its SAD is within 4x the noise
+   * threshold AND it is a strict local minimum of the cost over its 8 full-sample neighbours (all inside the search range)
+   * AND it costs less than the zero vector (otherwise a stale vector could survive on a scene that has become static);
+   * quarter-sample refinement then runs as after a search. */
+  int pred_hit = 0;
+  if (search && prev_type == 1 && !getenv("B2V_REF_NO_TPRED")) {   /* the switch exists for A/B experiments only */
+    const int cdx = asr(prev_mvx + 2, 2), cdy = asr(prev_mvy + 2, 2);
+    if ((cdx || cdy) && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
+      uint32_t kc = 0, kmin = 0xffffffffu;
+      for (int j = -1; j <= 1; j++)
+        for (int i = -1; i <= 1; i++) {
+          int sad = 0;
+          for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) sad += iabs(cy[r * 16 + c] - win[16 + cdy + j + r][16 + cdx + i + c]);
+          const uint32_t cost = (uint32_t)(sad + lambda * (se_bits(4 * (cdx + i)) + se_bits(4 * (cdy + j))));
+          const uint32_t key = (cost << 11) | (uint32_t)((cdy + j + 16) * 32 + (cdx + i + 16));
+          if (i == 0 && j == 0) kc = key; else if (key < kmin) kmin = key;
+        }
+      const int sadc = (int)(kc >> 11) - lambda * (se_bits(4 * cdx) + se_bits(4 * cdy));
+      const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (16 * 32 + 16);     /* ... and it must beat the zero vector */
+      if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; best = kc; }
+    }
+  }
   for (int dy = -16; search && dy <= 16; dy++)
     for (int dx = -16; dx <= 15; dx++) {
       int sad = 0;
@@ -676,7 +701,9 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   uint8_t Gp[22][22], bq[18][17], hq[17][18], jq[17][17];   /* Gp[v+3][u+3], bq[v+1][u+1], hq[v+1][u+1], jq[v+1][u+1] */
   /* not worth refining when the full-sample match is already within the quantisation noise of this QP */
   const int sad_int = (int)(best >> 11) - lambda * (se_bits(4 * bdx) + se_bits(4 * bdy));
-  if (search && iabs(bdx) <= 13 && iabs(bdy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda) {
+  /* a predictor hit whose previous vector was full-sample is not refined again: the previous refinement already preferred it */
+  const int pred_frac = pred_hit && ((prev_mvx | prev_mvy) & 3);
+  if ((search || pred_frac) && iabs(bdx) <= 13 && iabs(bdy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda) {
     int16_t b1[22][17];
     const int ox = 16 + bdx, oy = 16 + bdy;
     for (int v = -3; v <= 18; v++) for (int u = -3; u <= 18; u++) Gp[v + 3][u + 3] = win[oy + v][ox + u];

@@ -34,6 +34,7 @@ struct alignas(16) InterSm {      // one per warp; the 16-byte size padding keep
   alignas(4) uint8_t jq[17][24];   // centre half sample,            jq[Y+1][X+1], Y,X in [-1,15]
 };
 
+constexpr int ME_PRED_SAD_FACTOR = 4;      // temporal predictor accepted up to 4x the early-termination threshold (and only as a strict local minimum)
 constexpr int ME_FRAC_PENALTY_BITS = 4;   // fractional vectors pay 4 extra bits in the refinement cost
 
 // Table 8-12 as data: every fractional position is one plane sample or the rounded average of two.
@@ -140,12 +141,43 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   // ---- zero-motion early termination: co-located block within the quantisation noise of this QP ----
   const int lambda = me_lambda[qp];
   uint32_t best = (uint32_t)(16 * 32 + 16);      // candidate (0,0)
+  int sad0;
   {
     const uint32_t* w0p = &sm.win[16 + r8][4 + (c8 >> 2)];
     const uint32_t s0 = sad4acc(*reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), w0p[0],
                                 sad4acc(*reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]), w0p[1], 0u));
-    const int sad0 = __reduce_add_sync(FULL, (int)s0);
+    sad0 = __reduce_add_sync(FULL, (int)s0);
     if (sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda) best = 0xffffffffu;
+  }
+  // ---- temporal-predictor early termination (oracle/h264_ref.c encode_inter_mb): the vector this macroblock
+  // had in the previous picture, rounded to full samples (scrolling / panning content repeats it).  Accepted without the
+  // exhaustive search when its SAD is within 4x the noise threshold AND it is a strict local minimum of the cost over its 8
+  // full-sample neighbours AND it costs less than the zero vector; quarter-sample refinement then runs as after a search. ----
+  bool pred_hit = false, pred_frac = false;
+  if (best == 0xffffffffu) {
+    const MbInfo prev = f.mbinfo[mb];                       // still the previous picture's record: rewritten at the end of this kernel
+    const int cdx = (prev.mvx + 2) >> 2, cdy = (prev.mvy + 2) >> 2;
+    if (prev.type == MB_P16 && (cdx | cdy) != 0 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
+      const uint32_t c0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), c1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
+      uint32_t kc = 0, kmin = 0xffffffffu;
+#pragma unroll
+      for (int j = -1; j <= 1; j++) {
+#pragma unroll
+        for (int i = -1; i <= 1; i++) {
+          const int bx = 16 + cdx + i + c8;
+          const uint32_t* wr = &sm.win[16 + cdy + j + r8][bx >> 2];
+          const int sh = (bx & 3) * 8;
+          const uint32_t a0 = __funnelshift_r(wr[0], wr[1], sh), a1 = __funnelshift_r(wr[1], wr[2], sh);
+          const int sad = __reduce_add_sync(FULL, (int)sad4acc(c0, a0, sad4acc(c1, a1, 0u)));
+          const uint32_t cost = (uint32_t)(sad + lambda * (se_bits_dev(4 * (cdx + i)) + se_bits_dev(4 * (cdy + j))));
+          const uint32_t key = (cost << 11) | (uint32_t)((cdy + j + 16) * 32 + (cdx + i + 16));
+          if (i == 0 && j == 0) kc = key; else kmin = min(kmin, key);
+        }
+      }
+      const int sadc = (int)(kc >> 11) - lambda * (se_bits_dev(4 * cdx) + se_bits_dev(4 * cdy));
+      const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (uint32_t)(16 * 32 + 16);   // ... and it must beat the zero vector
+      if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { best = kc; pred_hit = true; pred_frac = ((prev.mvx | prev.mvy) & 3) != 0; }
+    }
   }
   const bool searched = best == 0xffffffffu;
   if (searched) {
@@ -187,8 +219,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   int mvx = 4 * dx, mvy = 4 * dy;
   // refine only inside the window (6-tap support [-3,+18]) and when the full-sample match is not already within the
   // quantisation noise of this QP (same threshold as the zero-motion early termination)
-  const int sad_int = searched ? (int)(best >> 11) - lambda * (se_bits_dev(4 * dx) + se_bits_dev(4 * dy)) : 0;
-  const bool refine = searched && abs(dx) <= 13 && abs(dy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda;
+  const int sad_int = (searched || pred_hit) ? (int)(best >> 11) - lambda * (se_bits_dev(4 * dx) + se_bits_dev(4 * dy)) : 0;
+  // a predictor hit whose previous vector was full-sample is not refined again: the previous refinement already preferred it
+  const bool refine = (searched || pred_frac) && abs(dx) <= 13 && abs(dy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda;
   const int ox = dxi, oy = dyi;                                        // window coordinates of the full-sample position
   if (refine) {
     // half-sample planes
