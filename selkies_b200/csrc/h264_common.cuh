@@ -322,6 +322,21 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
       t.lvs[17 + comp][b] = (int16_t)cdc_level;
     }
   }
+  // ---- inter macroblock whose every level quantised to zero (most of a desktop picture): the reconstruction is the
+  // prediction, nothing is coded; skip the inverse transform, the level stores and the size estimate ----
+  if (!INTRA16) {
+    const unsigned any_ac = __ballot_sync(FULL, n > 0), any_dc = __ballot_sync(FULL, is_chroma && cdc_level != 0);
+    if ((any_ac | any_dc) == 0u) {
+      if (is_luma) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) *reinterpret_cast<uint32_t*>(&t.rec_y[by + i][bx]) = *reinterpret_cast<const uint32_t*>(&t.pred_y[by + i][bx]);
+      }
+      reinterpret_cast<uint32_t*>(&t.rec_uv[0][0])[lane] = reinterpret_cast<const uint32_t*>(&t.pred_uv[0][0])[lane];
+      if (lane < 24) nnz_mb[lane] = 0;
+      luma_bits = 0; chroma_bits = 0;
+      return 0;
+    }
+  }
   // ---- reconstruction into the tile -------------------------------------------------------------
   int resid[16];
   if (is_luma) {

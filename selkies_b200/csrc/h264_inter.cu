@@ -303,6 +303,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
     const int cwc = f.cw >> 1;
     const int ya = clip3i(ylo >> 1, yhi >> 1, mby * 8 + yi + rc4), yb = clip3i(ylo >> 1, yhi >> 1, mby * 8 + yi + rc4 + 1);
     uint32_t out = 0;
+    if ((xf | yf) == 0) {     // full-sample chroma position (static and most scrolling content): the (Cb,Cr) pairs are copied
+#pragma unroll
+      for (int px = 0; px < 2; px++) {
+        const int xa = clip3i(0, cwc - 1, mbx * 8 + xi + (lane & 3) * 2 + px);
+        out |= (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(ref_uv + (size_t)ya * f.cw + xa * 2)) << (16 * px);
+      }
+    } else
 #pragma unroll
     for (int px = 0; px < 2; px++) {
       const int x = (lane & 3) * 2 + px;

@@ -12,16 +12,17 @@ from tests import synth
 pytestmark = pytest.mark.gpu
 
 
-def run_both(w, h, frames, stripe_rows, slice_rows, *, qp=28, rc_mode=N.B2V_RC_CQP, kbps=0, fps=30.0, idr_at=(0,), header_mode=N.B2V_HDR_NONE):
+def run_both(w, h, frames, stripe_rows, slice_rows, *, qp=28, rc_mode=N.B2V_RC_CQP, kbps=0, fps=30.0, idr_at=(0,), header_mode=N.B2V_HDR_NONE, paint=(0, 18)):
     enc = oracle.RefEncoder(w, h, slice_rows)
     enc.set_stripes(stripe_rows)
+    enc.set_paintover(*paint)
     target = int(kbps * 1000 / fps) if kbps else 0
     ref = []                       # per picture: [(y_start, bytes)] of the coded bands
     for i, f in enumerate(frames):
         au = enc.encode_bgra(f, i in idr_at, rc_mode=1 if rc_mode == N.B2V_RC_CQP else 0, qp=qp, target_bits=target)
         ref.append([(k * stripe_rows * 16, au[o:o + sz]) for k, (o, sz, c) in enumerate(enc.stripe_table()) if c])
     with Session(w, h, rc_mode=rc_mode, crf=qp, bitrate_kbps=kbps or 8000, fps=fps, slice_rows=slice_rows, gop=-1,
-                 stripe_rows=stripe_rows, header_mode=header_mode) as s:
+                 stripe_rows=stripe_rows, header_mode=header_mode, paintover_trigger_frames=paint[0], paintover_crf=paint[1]) as s:
         for i, f in enumerate(frames):
             if i in idr_at and i > 0:
                 s.flush()
