@@ -35,7 +35,7 @@ W, H = 3840, 2160
 FPS_NOMINAL = 60.0
 BITRATE_KBPS = 20000
 FRAMES_PER_STEP = 16
-N_DISTINCT = 8            # distinct input frames cycled: 8 x 33.2 MB = 265 MB > 126 MB of L2
+N_DISTINCT = 16           # distinct input frames cycled (the scroll restarts every 16 pictures): 16 x 33.2 MB = 531 MB > 126 MB of L2
 ALG_BYTES_PER_PX = 5.5    # 4 B BGRA read + 1 B Y + 0.5 B CbCr written
 
 
@@ -45,17 +45,19 @@ def synth_frames(n, w=W, h=H):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  One nvidia-smi process
+    (rank 0 only, all GPUs of the job, 50 ms period) is started before the warm-up so that it is already streaming when the
+    timed region begins; `mark()` / `stop()` delimit the rows that fall inside it."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, n_gpus: int):
+        self.n_gpus, self.rows, self.proc, self.t_mark = n_gpus, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -63,28 +65,41 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t_mark = time.monotonic()
 
     def stop(self):
+        t_end = time.monotonic()
         if self.proc:
+            time.sleep(0.06)                 # let the sample that was being taken at t_end arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+        mine = [(t, r) for t, r in self.rows if len(r) >= 8 and r[0].isdigit() and int(r[0]) < self.n_gpus]
+        inside = [r for t, r in mine if self.t_mark is not None and self.t_mark <= t <= t_end + 0.06]
+        window = "timed region"
+        if not inside and mine:              # region shorter than one sampling period: the samples bracketing it
+            t0 = self.t_mark if self.t_mark is not None else t_end
+            near = sorted(mine, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t_end)))[: 2 * self.n_gpus]
+            inside, window = [r for _, r in near], "nearest samples (region shorter than the 50 ms period)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "window": window, "gpus_sampled": self.n_gpus}
 
 
 def measured_peak():
@@ -166,7 +181,7 @@ def run_reference(args, rank, world):
     """CPU arm: the oracle port on all host threads; a step = 1 P picture of the same workload."""
     if rank != 0:
         return
-    frames = synth_frames(min(N_DISTINCT, 4))
+    frames = synth_frames(N_DISTINCT)          # the same cycle of pictures as the GPU arm
     import oracle
     cores = oracle.set_threads(usable_threads())
     enc = oracle.RefEncoder(W, H)
@@ -189,7 +204,7 @@ def run_reference(args, rank, world):
                                    "the reference's videoconvert+x264enc is absent from this image"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def rtp_leg(aus):
@@ -224,7 +239,26 @@ def workload_config(frames_per_step):
             "l2_policy": f"inputs larger than L2: {N_DISTINCT} distinct frames x 33.2 MB cycled", "parallelism": "one independent session per GPU (no collective)"}
 
 
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """stdout carries exactly ONE line (the JSON result): everything else that writes to fd 1 — NCCL's version banner, library
+    chatter of any rank — is sent to stderr from here on."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -264,6 +298,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_over_ranks(x: float):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def sum_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -293,14 +335,17 @@ def main():
         for j in range(FRAMES_PER_STEP):
             sess.submit_resident((k0 + j) % N_DISTINCT)
 
+    clocks = ClockSampler(world) if rank == 0 else None
+    if clocks:
+        clocks.start()
     k = 0
     for _ in range(args.warmup):
         step_resident(k); k += FRAMES_PER_STEP
     sess.flush()
     sess.reset_stats()
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.mark()
     sess.timer_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -311,6 +356,7 @@ def main():
     st = sess.stats()
     n_frames = args.steps * FRAMES_PER_STEP
     t_ms = max_over_ranks(max(dev_ms, 0.0))
+    per_rank_ms = gather_over_ranks(max(dev_ms, 0.0))
     value = sum_over_ranks(float(n_frames)) / (t_ms / 1000.0)
 
     # ---------------- leg 2: end to end from pinned host buffers -----------------------------------------
@@ -340,7 +386,7 @@ def main():
     e2e_dev_ms = sess.timer_stop()
     e2e_wall_ms = 1000 * (time.perf_counter() - t0)
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     st1 = sess.stats()
     e2e_ms = max_over_ranks(max(e2e_wall_ms, e2e_dev_ms))
     e2e_value = sum_over_ranks(float(n_frames)) / (e2e_ms / 1000.0)
@@ -454,9 +500,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "wall_ms": e2e_wall_ms, "device_ms": e2e_dev_ms, "access_unit_bytes_per_frame": out_bytes[0] / max(1, n_frames)},
             "gpu_launches": int(st["kernel_launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "kernels_us": kern, "numa_node": numa, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus), "striped_mode": striped,
+            "kernels_us": kern, "per_rank_ms_resident": per_rank_ms, "numa_node": numa, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus), "striped_mode": striped,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
