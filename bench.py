@@ -34,8 +34,9 @@ sys.path.insert(0, ROOT)
 W, H = 3840, 2160
 FPS_NOMINAL = 60.0
 BITRATE_KBPS = 20000
-FRAMES_PER_STEP = 16
+FRAMES_PER_STEP = 64      # one step = one batch of 64 pictures through the hot path (long enough that host scheduling jitter averages out)
 N_DISTINCT = 16           # distinct input frames cycled (the scroll restarts every 16 pictures): 16 x 33.2 MB = 531 MB > 126 MB of L2
+N_SIDE = 256              # pictures in each side measurement (device-timer pass, striped mode)
 ALG_BYTES_PER_PX = 5.5    # 4 B BGRA read + 1 B Y + 0.5 B CbCr written
 
 
@@ -315,7 +316,7 @@ def main():
 
     frames = synth_frames(N_DISTINCT)
     peak, peak_src = measured_peak()
-    flags = N.B2V_FLAG_TIMING
+    flags = N.B2V_FLAG_TIMING_CSC     # timed legs: one CUDA-event pair per picture, around the CSC launch (the roofline kernel)
     sess = Session(W, H, fps=FPS_NOMINAL, device=local_rank, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS,
                    ring_slots=N_DISTINCT, flags=flags, collect=False)
     out_bytes = [0]
@@ -343,6 +344,8 @@ def main():
         step_resident(k); k += FRAMES_PER_STEP
     sess.flush()
     sess.reset_stats()
+    import gc
+    gc.disable()                 # no collector pauses inside the timed regions
     barrier()
     if clocks:
         clocks.mark()
@@ -415,22 +418,39 @@ def main():
                          flags=N.B2V_FLAG_TIMING | N.B2V_FLAG_DEVICE_TIMER, collect=False) as sd:
                 for i, f in enumerate(frames):
                     sd.resident_upload(i, f)
-                for kk in range(3 * FRAMES_PER_STEP):
+                for kk in range(48):
                     sd.submit_resident(kk % N_DISTINCT)
                 sd.flush(); sd.reset_stats()
-                for kk in range(8 * FRAMES_PER_STEP):
+                for kk in range(N_SIDE):
                     sd.submit_resident(kk % N_DISTINCT)
                 sd.flush()
                 sdt = sd.stats()
             if sdt["n_csc_device"]:
                 us = sdt["ms_csc_device"] / sdt["n_csc_device"] * 1e3
-                roofline["device_timer"] = {"note": "in-step launches timed by the kernel itself (%globaltimer), 128 pictures, separate instrumented pass",
+                roofline["device_timer"] = {"note": "in-step launches timed by the kernel itself (%globaltimer), 256 pictures, separate instrumented pass",
                                             "us_per_launch": us, "achieved": alg / (us * 1e-6) / 1e9, "frac": alg / (us * 1e-6) / 1e9 / peak,
                                             "frac_of_8TBps_nominal": alg / (us * 1e-6) / 1e9 / 8000.0}
         except Exception as e:
             roofline["device_timer"] = {"error": repr(e)}
-    kern = {k: (st["ms_" + k] / max(1, st["n_" + k])) * 1e3 for k in ("csc", "intra", "inter", "cavlc", "slice", "pack")}
-    kern["gpu_span_per_frame"] = st["ms_total_gpu"] / max(1, st["n_csc"]) * 1e3
+    # per-kernel breakdown: separate pass with every stage bracketed by events (those extra event commands cost the step 4-5 %,
+    # so they stay out of the timed legs)
+    with Session(W, H, fps=FPS_NOMINAL, device=local_rank, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS, ring_slots=4,
+                 flags=N.B2V_FLAG_TIMING, collect=False) as sk:
+        for i, f in enumerate(frames):
+            sk.resident_upload(i, f)
+        for kk in range(48):
+            sk.submit_resident(kk % N_DISTINCT)
+        sk.flush(); sk.reset_stats()
+        for kk in range(N_SIDE):
+            sk.submit_resident(kk % N_DISTINCT)
+        sk.flush()
+        stk = sk.stats()
+    kern = {k: (stk["ms_" + k] / max(1, stk["n_" + k])) * 1e3 for k in ("csc", "intra", "inter", "cavlc", "slice", "pack")}
+    kern["gpu_span_per_frame"] = stk["ms_total_gpu"] / max(1, stk["n_csc"]) * 1e3
+    kern["note"] = f"separate instrumented pass, {N_SIDE} pictures, every stage between CUDA events"
+    per_rank_span = gather_over_ranks(kern["gpu_span_per_frame"])
+    per_rank_inter = gather_over_ranks(kern["inter"])
+    per_rank_numa = gather_over_ranks(float(-1 if numa is None else numa))
     sess.close()
     # BASELINE config 4 (7680x4320 CSC roofline stress): same kernel, one event pair per launch, 4 frames x 132.7 MB cycled
     if rank == 0:
@@ -465,16 +485,16 @@ def main():
                 ss._on_frame = on_stripe
                 for i, f in enumerate(frames):
                     ss.resident_upload(i, f)
-                for kk in range(3 * FRAMES_PER_STEP):
+                for kk in range(48):
                     ss.submit_resident(kk % N_DISTINCT)
                 ss.flush(); n_cb[0] = n_str[0] = 0
                 ss.timer_start()
-                for kk in range(8 * FRAMES_PER_STEP):
+                for kk in range(N_SIDE):
                     ss.submit_resident(kk % N_DISTINCT)
                 ms = ss.timer_stop()
-            striped = {"stripe_rows": rows, "stripes_per_picture": -(-(H // 16) // rows), "value": 8 * FRAMES_PER_STEP / (ms / 1000.0), "unit": "frames/s",
-                       "stripes_delivered_per_picture": n_cb[0] / (8 * FRAMES_PER_STEP), "bytes_per_picture": n_str[0] / (8 * FRAMES_PER_STEP),
-                       "note": "inputs resident in HBM, 128 pictures; stripes whose macroblocks were all skipped are not delivered"}
+            striped = {"stripe_rows": rows, "stripes_per_picture": -(-(H // 16) // rows), "value": N_SIDE / (ms / 1000.0), "unit": "frames/s",
+                       "stripes_delivered_per_picture": n_cb[0] / N_SIDE, "bytes_per_picture": n_str[0] / N_SIDE,
+                       "note": "inputs resident in HBM, 256 pictures; stripes whose macroblocks were all skipped are not delivered"}
         except Exception as e:
             striped = {"error": repr(e)}
 
@@ -500,7 +520,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "wall_ms": e2e_wall_ms, "device_ms": e2e_dev_ms, "access_unit_bytes_per_frame": out_bytes[0] / max(1, n_frames)},
             "gpu_launches": int(st["kernel_launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "kernels_us": kern, "per_rank_ms_resident": per_rank_ms, "numa_node": numa, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus), "striped_mode": striped,
+            "kernels_us": kern, "per_rank_ms_resident": per_rank_ms, "per_rank_span_us": per_rank_span, "per_rank_inter_us": per_rank_inter, "per_rank_numa": per_rank_numa, "numa_node": numa, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus), "striped_mode": striped,
         }
         emit(line)
     if world > 1:

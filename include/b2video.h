@@ -82,7 +82,8 @@ enum {
   B2V_FLAG_SPS_EVERY_IDR = 1,   /* in-band SPS/PPS before every IDR (rtc.py:394-401); always on */
   B2V_FLAG_NO_ENCODE     = 2,   /* CSC only (BASELINE config 4: 8K CSC roofline stress)         */
   B2V_FLAG_TIMING        = 4,   /* bracket every kernel with CUDA events (b2v_get_stats)        */
-  B2V_FLAG_DEVICE_TIMER  = 8    /* with TIMING: the CSC kernel also stamps %globaltimer (ms_csc_device) */
+  B2V_FLAG_DEVICE_TIMER  = 8,   /* with TIMING: the CSC kernel also stamps %globaltimer (ms_csc_device) */
+  B2V_FLAG_TIMING_CSC    = 16   /* one CUDA-event pair per picture, around the CSC launch only (ms_csc)  */
 };
 
 /* One encoded frame, the native image of the pixelflux callback result

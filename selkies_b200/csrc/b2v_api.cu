@@ -50,7 +50,7 @@ struct Session {
   b2v_settings cfg{};
   int device = 0, sm_count = 148;
   int src_w = 0, src_h = 0, dst_w = 0, dst_h = 0, coded_w = 0, coded_h = 0;
-  bool encode = true, timing = false;
+  bool encode = true, timing = false, timing_csc_only = false;
   cudaStream_t st_copy = nullptr, st_enc = nullptr, st_out = nullptr;
 
   // ingest ring
@@ -224,7 +224,8 @@ void output_loop(Session* s) {
       cudaEvent_t* ev = s->ev_t[j.out_idx];
       float ms[6] = {0, 0, 0, 0, 0, 0};
       cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
-      if (s->encode) {
+      const bool stages = s->encode && !s->timing_csc_only;
+      if (stages) {
         for (int k = 1; k < 5; k++) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
         cudaEventElapsedTime(&ms[5], ev[0], ev[5]);
       } else ms[5] = ms[0];
@@ -234,7 +235,7 @@ void output_loop(Session* s) {
         const AuHeader* ah2 = (const AuHeader*)s->h_out[j.out_idx];
         if (ah2->csc_t1 > ah2->csc_t0 && ah2->csc_t0 != 0) { s->stats.ms_csc_device += (double)(ah2->csc_t1 - ah2->csc_t0) * 1e-6; s->stats.n_csc_device++; }
       }
-      if (s->encode) {
+      if (stages) {
         if (j.is_key) { s->stats.ms_intra += ms[1]; s->stats.n_intra++; }
         else { s->stats.ms_inter += ms[1]; s->stats.n_inter++; }
         s->stats.ms_cavlc += ms[2]; s->stats.n_cavlc++;
@@ -337,7 +338,7 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
   if (in_slot >= 0) CK(cudaEventRecord(s->ev_csc[in_slot], s->st_enc));
   CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
   if (s->encode) {
-    fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = ev; fp.csc_ts = cp.ts;
+    fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = s->timing_csc_only ? nullptr : ev; fp.csc_ts = cp.ts;
     nl += encoder_encode(s->enc, &fp, s->st_enc);
     CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
     CK(cudaStreamWaitEvent(s->st_out, s->ev_enc[out_idx], 0));
@@ -385,7 +386,8 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   s->cfg = *cfg; s->device = cfg->device;
   s->src_w = sw; s->src_h = sh; s->dst_w = dw; s->dst_h = dh;
   s->encode = !(cfg->flags & B2V_FLAG_NO_ENCODE);
-  s->timing = (cfg->flags & B2V_FLAG_TIMING) != 0;
+  s->timing = (cfg->flags & (B2V_FLAG_TIMING | B2V_FLAG_TIMING_CSC)) != 0;
+  s->timing_csc_only = s->timing && !(cfg->flags & B2V_FLAG_TIMING);
   s->n_slots = cfg->ring_slots > 0 ? cfg->ring_slots : 4;
   if (s->n_slots < 2) s->n_slots = 2;
   if (s->n_slots > kMaxSlots) s->n_slots = kMaxSlots;
@@ -403,8 +405,10 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   for (int i = 0; i < kMaxSlots; i++) {
     cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s->ev_csc[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming);
+    // the output thread sleeps on these (blocking sync) instead of spinning: one busy core per session would eat the host's
+    // CPU budget when eight sessions share a box
+    cudaEventCreateWithFlags(&s->ev_enc[i], cudaEventDisableTiming | cudaEventBlockingSync);
+    cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming | cudaEventBlockingSync);
   }
   for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventCreate(&s->ev_t[i][k]);
   cudaEventCreate(&s->ev_timer[0]); cudaEventCreate(&s->ev_timer[1]);
