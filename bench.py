@@ -141,20 +141,23 @@ def bind_to_gpu_numa_node(torch, device: int):
 
 
 def csc_dram_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one 4K CSC launch, from the committed `ncu --set full` capture
-    (profiles/r1_ncu_full_raw.csv).  The 12.4 MB NV12 output stays in L2, so traffic ~= the 33.2 MB BGRA input."""
+    """(total, read, write, file) DRAM bytes of one 4K CSC launch from the newest committed `ncu --set full` capture under
+    profiles/.  The read side is exactly the 33.2 MB BGRA input (no re-reads); the 12.4 MB NV12 output stays in L2 for the
+    encoder kernels that follow (write side: a few KB), so traffic < algorithmic bytes."""
     try:
-        import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_raw.csv"))))
+        import csv, glob
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_v*_raw.csv")), key=lambda p: (len(p), p))
+        rows = list(csv.reader(open(files[-1])))
         hdr, units = rows[0], rows[1]
         ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for r in rows[2:]:
             if "csc_bgra_nv12" in r[ik]:
-                return float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1)
+                rd, wr = float(r[ir]) * scale.get(units[ir], 1), float(r[iw]) * scale.get(units[iw], 1)
+                return rd + wr, rd, wr, os.path.basename(files[-1])
     except Exception:
         pass
-    return None
+    return None, None, None, None
 
 
 def usable_threads() -> int:
@@ -401,12 +404,13 @@ def main():
     csc_ms = st["ms_csc"] / max(1, st["n_csc"])
     achieved = alg / (csc_ms * 1e-3) / 1e9 if csc_ms > 0 else 0.0
     burst_ms = sess.bench_csc_burst(N_DISTINCT, 200)
+    traffic = csc_dram_traffic()
     roofline = {"bound": "hbm", "kernel": "csc_bgra_nv12_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": csc_dram_traffic(),
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic[0], "traffic_read": traffic[1], "traffic_write": traffic[2], "traffic_source": traffic[3],
                 "algorithmic_bytes_per_launch": alg, "us_per_launch": csc_ms * 1e3,
                 "device_timer": None,
                 "frac_of_8TBps_nominal": achieved / 8000.0,
-                "burst": {"note": "200 back-to-back launches between one event pair, same 8 cycled frames",
+                "burst": {"note": f"200 back-to-back launches between one event pair, same {N_DISTINCT} cycled frames",
                           "us_per_launch": burst_ms * 1e3, "achieved": alg / (burst_ms * 1e-3) / 1e9,
                           "frac": alg / (burst_ms * 1e-3) / 1e9 / peak}}
     # the same step with the CSC kernel stamping %globaltimer itself (first block start .. last block end): shows what the
