@@ -357,6 +357,27 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
   return 0;
 }
 
+// everything b2v_create made, in reverse; also the failure path of b2v_create
+void release_session(Session* s) {
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  free_geometry(s);
+  for (int i = 0; i < kMaxSlots; i++) {
+    if (s->ev_h2d[i]) cudaEventDestroy(s->ev_h2d[i]);
+    if (s->ev_csc[i]) cudaEventDestroy(s->ev_csc[i]);
+    if (s->ev_enc[i]) cudaEventDestroy(s->ev_enc[i]);
+    if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+    for (int k = 0; k < 8; k++) if (s->ev_t[i][k]) cudaEventDestroy(s->ev_t[i][k]);
+  }
+  if (s->ev_timer[0]) cudaEventDestroy(s->ev_timer[0]);
+  if (s->ev_timer[1]) cudaEventDestroy(s->ev_timer[1]);
+  if (s->d_csc_ts) cudaFree(s->d_csc_ts);
+  if (s->st_copy) cudaStreamDestroy(s->st_copy);
+  if (s->st_enc) cudaStreamDestroy(s->st_enc);
+  if (s->st_out) cudaStreamDestroy(s->st_out);
+  delete s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -414,7 +435,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   cudaEventCreate(&s->ev_timer[0]); cudaEventCreate(&s->ev_timer[1]);
   if (s->timing && (cfg->flags & B2V_FLAG_DEVICE_TIMER)) cudaMalloc((void**)&s->d_csc_ts, sizeof(unsigned long long) * 2 * kMaxSlots);
   int rc = alloc_geometry(s);
-  if (rc) { free_geometry(s); delete s; return rc; }
+  if (rc) { release_session(s); return rc; }
   s->out_thread = std::thread(output_loop, s);
   *out = s;
   return 0;
@@ -430,18 +451,7 @@ void b2v_destroy(void* h) {
   }
   s->cv_job.notify_all(); s->cv_slot.notify_all();
   if (s->out_thread.joinable()) s->out_thread.join();
-  cudaSetDevice(s->device);
-  cudaDeviceSynchronize();
-  free_geometry(s);
-  for (int i = 0; i < kMaxSlots; i++) {
-    cudaEventDestroy(s->ev_h2d[i]); cudaEventDestroy(s->ev_csc[i]);
-    cudaEventDestroy(s->ev_enc[i]); cudaEventDestroy(s->ev_out[i]);
-  }
-  for (int i = 0; i < kMaxSlots; i++) for (int k = 0; k < 8; k++) cudaEventDestroy(s->ev_t[i][k]);
-  cudaEventDestroy(s->ev_timer[0]); cudaEventDestroy(s->ev_timer[1]);
-  if (s->d_csc_ts) cudaFree(s->d_csc_ts);
-  cudaStreamDestroy(s->st_copy); cudaStreamDestroy(s->st_enc); cudaStreamDestroy(s->st_out);
-  delete s;
+  release_session(s);
 }
 
 void* b2v_ring_acquire(void* h, int32_t* slot) {

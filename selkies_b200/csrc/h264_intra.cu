@@ -1,11 +1,13 @@
 // h264_intra.cu — IDR pictures: Intra4x4 / Intra16x16 macroblocks (ITU-T H.264 8.3.1, 8.3.3 luma; 8.3.4 chroma).
 //
-// One warp per macroblock ROW: intra prediction needs the reconstructed left neighbour, so the
+// One block of TWO warps per macroblock ROW: intra prediction needs the reconstructed left neighbour, so the
 // macroblocks of a row are a serial chain; rows of the same slice additionally wait for the row above
 // (wavefront, two macroblocks of lag because Intra4x4 reads the above-right samples) through a progress
 // counter in global memory.  With the default slice_rows = 1 every row is its own slice and all rows run in parallel.
+// The chain is latency-bound (one dependent shuffle / shared-memory round trip after the other), so the two ways of
+// coding a macroblock run side by side: warp 0 codes Intra16x16 + chroma while warp 1 runs the Intra4x4 pass.
 //
-// Per macroblock the warp codes the luma BOTH ways and keeps the better one:
+// Per macroblock the luma is coded BOTH ways and the better one kept:
 //   Intra4x4   16 blocks in decoding order; per block the 32 lanes evaluate 8 modes x 4 rows (+ horizontal-up)
 //              in parallel, key = (SAD + lambda*(mode == predicted ? 1 : 4))*16 + mode, then lanes 0..15 hold one
 //              residual sample each and run the 4x4 transform / quantisation / reconstruction with warp shuffles
@@ -81,11 +83,50 @@ __device__ __forceinline__ int inv1(int k, int p0, int p1, int p2, int p3) {
   return k == 0 ? e0 + e3 : k == 1 ? e1 + e2 : k == 2 ? e1 - e2 : e0 - e3;
 }
 
-__global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
+// Intra16x16 luma mode decision (8.3.3): key = SAD*4 + mode over the available modes; p0/p1 = this lane's 8 predicted samples
+struct I16Dec { int key, mode; uint32_t p0, p1; };
+__device__ __forceinline__ I16Dec i16_decide(const IntraNb& nb, const MbTile& t, int lane, bool has_top, bool has_left) {
+  const int r8 = lane >> 1, c8 = (lane & 1) * 8;
+  const uint32_t cy0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]);
+  const uint32_t cy1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
+  int sum_t = 0, sum_l = 0, H = 0, V = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) { sum_t += nb.top_y[i]; sum_l += nb.left_y[i]; }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    H += (i + 1) * ((int)nb.top_y[8 + i] - (i == 7 ? nb.tl_y : (int)nb.top_y[6 - i]));
+    V += (i + 1) * ((int)nb.left_y[8 + i] - (i == 7 ? nb.tl_y : (int)nb.left_y[6 - i]));
+  }
+  const int dc_y = has_top && has_left ? (sum_t + sum_l + 16) >> 5 : has_top ? (sum_t + 8) >> 4 : has_left ? (sum_l + 8) >> 4 : 128;
+  const int pa = 16 * ((int)nb.left_y[15] + (int)nb.top_y[15]), pb = (5 * H + 32) >> 6, pc = (5 * V + 32) >> 6;
+  uint32_t pv0 = *reinterpret_cast<const uint32_t*>(&nb.top_y[c8]), pv1 = *reinterpret_cast<const uint32_t*>(&nb.top_y[c8 + 4]);
+  uint32_t ph = rep4(nb.left_y[r8]), pd = rep4(dc_y), pp0 = 0, pp1 = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    pp0 |= (uint32_t)clip255((pa + pb * (c8 + j - 7) + pc * (r8 - 7) + 16) >> 5) << (8 * j);
+    pp1 |= (uint32_t)clip255((pa + pb * (c8 + 4 + j - 7) + pc * (r8 - 7) + 16) >> 5) << (8 * j);
+  }
+  int best_key = 0x7fffffff, best_mode = 2, s;
+  if (has_top) { s = __reduce_add_sync(FULL, __vsadu4(cy0, pv0) + __vsadu4(cy1, pv1)); if (s * 4 + 0 < best_key) { best_key = s * 4 + 0; best_mode = 0; } }
+  if (has_left) { s = __reduce_add_sync(FULL, __vsadu4(cy0, ph) + __vsadu4(cy1, ph)); if (s * 4 + 1 < best_key) { best_key = s * 4 + 1; best_mode = 1; } }
+  s = __reduce_add_sync(FULL, __vsadu4(cy0, pd) + __vsadu4(cy1, pd)); if (s * 4 + 2 < best_key) { best_key = s * 4 + 2; best_mode = 2; }
+  if (has_top && has_left) { s = __reduce_add_sync(FULL, __vsadu4(cy0, pp0) + __vsadu4(cy1, pp1)); if (s * 4 + 3 < best_key) { best_key = s * 4 + 3; best_mode = 3; } }
+  I16Dec d;
+  d.key = best_key; d.mode = best_mode;
+  d.p0 = best_mode == 0 ? pv0 : best_mode == 1 ? ph : best_mode == 2 ? pd : pp0;
+  d.p1 = best_mode == 0 ? pv1 : best_mode == 1 ? ph : best_mode == 2 ? pd : pp1;
+  return d;
+}
+
+// what the Intra4x4 warp hands to the deciding warp
+struct I4Result { int tried, mode_bits, cbp, bits; long long d; };
+
+__global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
   __shared__ __align__(16) MbTile t;
   __shared__ __align__(16) IntraNb nb;
   __shared__ __align__(16) I4State i4;
-  const int lane = threadIdx.x, mby = blockIdx.x;
+  __shared__ I4Result r4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, mby = blockIdx.x;
   const int qp = frame_qp(f);
   const int lambda = me_lambda[qp];
   const bool has_top = top_in_slice(f, mby);
@@ -102,9 +143,9 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
   const int izz = (int)((0xFEA9DB83C7426510ull >> (4 * rpos)) & 15ull);      // raster -> scan position (inverse zig-zag), nibble-packed
   const int lm = lane >> 2, ly = lane & 3;                                    // candidate mode / row evaluated by this lane
   const int lm_need = (lm == 0 || lm == 3 || lm == 7) ? 0 : lm == 1 ? 1 : lm == 2 ? 2 : 3;   // needs: above / left / nothing / all three
-  if (lane < 4) nb.left_modes[lane] = 2;
-  for (int i = lane; i < 144; i += 32) (&i4.code[0][0])[i] = (&i4_pred_code[0][0])[i];
-  __syncwarp();
+  if (threadIdx.x < 4) nb.left_modes[threadIdx.x] = 2;
+  for (int i = threadIdx.x; i < 144; i += 64) (&i4.code[0][0])[i] = (&i4_pred_code[0][0])[i];
+  __syncthreads();
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(&i4.code[lm][ly * 4]);   // V-indices of this lane's four predicted samples
   const uint32_t ch = *reinterpret_cast<const uint32_t*>(&i4.code[8][ly * 4]);    // ... for horizontal-up
 
@@ -113,11 +154,11 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
     const bool has_left = mbx > 0;
     const bool has_tr = has_top && mbx + 1 < f.mbw;
     if (has_top) {       // wavefront: the row above must have finished macroblock mbx+1 (above-right samples)
-      if (lane == 0) { const int need = min(mbx + 2, f.mbw); while (*((volatile int*)&f.progress[mby - 1]) < need) { } __threadfence(); }
-      __syncwarp();
+      if (threadIdx.x == 0) { const int need = min(mbx + 2, f.mbw); while (*((volatile int*)&f.progress[mby - 1]) < need) { } __threadfence(); }
+      __syncthreads();
     }
-    // ---- load current macroblock and neighbours --------------------------------------------------
-    {
+    // ---- load current macroblock and neighbours (warp 0) ------------------------------------------
+    if (warp == 0) {
       const uint2 v = *reinterpret_cast<const uint2*>(cur_y + (size_t)(mby * 16 + r8) * f.cw + mbx * 16 + c8);
       *reinterpret_cast<uint2*>(&t.cur_y[r8][c8]) = v;
       if (lane < 16) {
@@ -141,7 +182,13 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
         }
       }
     }
-    __syncwarp();
+    __syncthreads();
+    int best_mode = 2, cbest = 0, cbp = 0, luma_bits16 = 0, chroma_bits = 0;
+    long long d16 = 0;
+    int16_t* coef_mb = f.coef + (size_t)mb * COEF_BLOCKS * 16;
+    uint8_t* nnz_mb = f.nnz + (size_t)mb * 32;
+    if (warp == 0) {
+    // ================= warp 0: Intra16x16 luma + chroma ==================================================
     // chroma DC predictors (8.3.4.1-3), one (component, block) per lane 0..7
     if (lane < 8) {
       const int c = lane >> 2, b = lane & 3, bx = (b & 1) * 4, by = (b >> 1) * 4;
@@ -154,39 +201,11 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
       else dc = has_left ? (sl + 2) >> 2 : has_top ? (st + 2) >> 2 : 128;
       nb.cdc[lane] = dc;
     }
-    // ---- Intra16x16 luma mode decision: key = SAD*4 + mode over available modes -------------------
-    const uint32_t cy0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]);
-    const uint32_t cy1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
-    int sum_t = 0, sum_l = 0, H = 0, V = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) { sum_t += nb.top_y[i]; sum_l += nb.left_y[i]; }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      H += (i + 1) * ((int)nb.top_y[8 + i] - (i == 7 ? nb.tl_y : (int)nb.top_y[6 - i]));
-      V += (i + 1) * ((int)nb.left_y[8 + i] - (i == 7 ? nb.tl_y : (int)nb.left_y[6 - i]));
-    }
-    const int dc_y = has_top && has_left ? (sum_t + sum_l + 16) >> 5 : has_top ? (sum_t + 8) >> 4 : has_left ? (sum_l + 8) >> 4 : 128;
-    const int pa = 16 * ((int)nb.left_y[15] + (int)nb.top_y[15]), pb = (5 * H + 32) >> 6, pc = (5 * V + 32) >> 6;
-    uint32_t pv0 = *reinterpret_cast<const uint32_t*>(&nb.top_y[c8]), pv1 = *reinterpret_cast<const uint32_t*>(&nb.top_y[c8 + 4]);
-    uint32_t ph = rep4(nb.left_y[r8]), pd = rep4(dc_y), pp0 = 0, pp1 = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      pp0 |= (uint32_t)clip255((pa + pb * (c8 + j - 7) + pc * (r8 - 7) + 16) >> 5) << (8 * j);
-      pp1 |= (uint32_t)clip255((pa + pb * (c8 + 4 + j - 7) + pc * (r8 - 7) + 16) >> 5) << (8 * j);
-    }
-    int best_key = 0x7fffffff, best_mode = 2;
     {
-      int s;
-      if (has_top) { s = __reduce_add_sync(FULL, __vsadu4(cy0, pv0) + __vsadu4(cy1, pv1)); if (s * 4 + 0 < best_key) { best_key = s * 4 + 0; best_mode = 0; } }
-      if (has_left) { s = __reduce_add_sync(FULL, __vsadu4(cy0, ph) + __vsadu4(cy1, ph)); if (s * 4 + 1 < best_key) { best_key = s * 4 + 1; best_mode = 1; } }
-      s = __reduce_add_sync(FULL, __vsadu4(cy0, pd) + __vsadu4(cy1, pd)); if (s * 4 + 2 < best_key) { best_key = s * 4 + 2; best_mode = 2; }
-      if (has_top && has_left) { s = __reduce_add_sync(FULL, __vsadu4(cy0, pp0) + __vsadu4(cy1, pp1)); if (s * 4 + 3 < best_key) { best_key = s * 4 + 3; best_mode = 3; } }
-    }
-    {
-      uint32_t p0 = best_mode == 0 ? pv0 : best_mode == 1 ? ph : best_mode == 2 ? pd : pp0;
-      uint32_t p1 = best_mode == 0 ? pv1 : best_mode == 1 ? ph : best_mode == 2 ? pd : pp1;
-      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = p0;
-      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = p1;
+      const I16Dec d = i16_decide(nb, t, lane, has_top, has_left);
+      best_mode = d.mode;
+      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = d.p0;
+      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = d.p1;
     }
     __syncwarp();   // nb.cdc visible
     // ---- chroma mode decision: key = (SAD Cb + SAD Cr)*4 + mode ------------------------------------
@@ -214,7 +233,8 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
         qp_ |= (uint32_t)clip255((a + b * (x0 + 1 - 3) + cq * (rc4 - 3) + 16) >> 5) << (16 + 8 * c);
       }
     }
-    int cbest_key = 0x7fffffff, cbest = 0;
+    int cbest_key = 0x7fffffff;
+    cbest = 0;
     {
       int s = __reduce_add_sync(FULL, __vsadu4(cc, qd)); if (s * 4 + 0 < cbest_key) { cbest_key = s * 4 + 0; cbest = 0; }
       if (has_left) { s = __reduce_add_sync(FULL, __vsadu4(cc, qh)); if (s * 4 + 1 < cbest_key) { cbest_key = s * 4 + 1; cbest = 1; } }
@@ -224,6 +244,18 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
     *reinterpret_cast<uint32_t*>(&t.pred_uv[rc4][cc4]) = cbest == 0 ? qd : cbest == 1 ? qh : cbest == 2 ? qv : qp_;
     __syncwarp();
 
+    // ---- Intra16x16 coding (also codes the chroma, which is identical either way) --------------------------
+    cbp = transform_mb<true>(t, lane, qp, coef_mb, nnz_mb, luma_bits16, chroma_bits);
+    __syncwarp();
+    {
+      int s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)t.rec_y[r8][c8 + j]; s += e * e; }
+      d16 = __reduce_add_sync(FULL, s);
+    }
+    } else {
+    // ================= warp 1: Intra4x4 candidate ===========================================================
+    const int best_key = i16_decide(nb, t, lane, has_top, has_left).key;      // same decision as warp 0 (reads only)
     // ---- Intra4x4 candidate: 16 blocks in decoding order ----------------------------------------------
     // rt = reconstruction with a one-sample frame: rt[y+1][x+1] is macroblock sample (x,y), row 0 / column 0 hold the
     // neighbours above (16 + 4 above-right) and to the left, rt[0][0] the above-left sample.
@@ -306,19 +338,14 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
         d4 = __reduce_add_sync(FULL, sd);
       }
     }
-    // ---- Intra16x16 coding (also codes the chroma, which is identical either way) --------------------------
-    int luma_bits16, chroma_bits;
-    int16_t* coef_mb = f.coef + (size_t)mb * COEF_BLOCKS * 16;
-    uint8_t* nnz_mb = f.nnz + (size_t)mb * 32;
-    int cbp = transform_mb<true>(t, lane, qp, coef_mb, nnz_mb, luma_bits16, chroma_bits);
-    __syncwarp();
-    long long d16;
-    {
-      int s = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)t.rec_y[r8][c8 + j]; s += e * e; }
-      d16 = __reduce_add_sync(FULL, s);
+    if (lane == 0) { r4.tried = try_i4; r4.mode_bits = mode_bits4; r4.cbp = cbp4; r4.bits = bits4_cavlc; r4.d = d4; }
     }
+    __syncthreads();
+    // ================= decision, commit and write-out (warp 0) ============================================
+    if (warp == 0) {
+    const bool try_i4 = r4.tried != 0;
+    const int mode_bits4 = r4.mode_bits, cbp4 = r4.cbp, bits4_cavlc = r4.bits;
+    const long long d4 = r4.d;
     const long long l2 = rd_lambda[qp];
     const bool use_i4 = try_i4 && d4 + l2 * (8 + bits4_cavlc + mode_bits4) < d16 + l2 * (8 + luma_bits16);
     int est;
@@ -356,19 +383,20 @@ __global__ void __launch_bounds__(32) k_intra_rows(FrameCtx f) {
         f.mbinfo[mb] = mi;
       }
     }
+    }
     if (signal_progress) {
       __threadfence();
-      __syncwarp();
-      if (lane == 0) *((volatile int*)&f.progress[mby]) = mbx + 1;
+      __syncthreads();
+      if (threadIdx.x == 0) *((volatile int*)&f.progress[mby]) = mbx + 1;
     } else {
-      __syncwarp();
+      __syncthreads();
     }
   }
 }
 
 int launch_intra(const FrameCtx& f, cudaStream_t st) {
   cudaMemsetAsync(f.progress, 0, sizeof(int) * f.mbh, st);
-  k_intra_rows<<<f.mbh, 32, 0, st>>>(f);
+  k_intra_rows<<<f.mbh, 64, 0, st>>>(f);
   return 1;
 }
 
