@@ -37,7 +37,8 @@ struct IntraNb {
 struct I4State {
   alignas(16) int16_t lv[16][16];            // [blkIdx][scan position]; read back with 16-byte loads
   alignas(16) uint8_t code[9][16];           // shared-memory copy of i4_pred_code (read as 32-bit words)
-  alignas(16) uint8_t v[64];                 // X | F2 | F3 | DC of the current block (see i4_pred_code)
+  alignas(16) uint8_t v[2][64];              // per Intra4x4 warp: X | F2 | F3 | DC of its current block (see i4_pred_code)
+  int mode_bits_part;                        // mode bits accumulated by the second Intra4x4 warp
   uint8_t rt[17][24];                        // framed reconstruction (see the Intra4x4 pass)
   uint8_t nnz[16];                           // raster block position
   uint8_t modes[16];                         // raster block position
@@ -121,7 +122,9 @@ __device__ __forceinline__ I16Dec i16_decide(const IntraNb& nb, const MbTile& t,
 // what the Intra4x4 warp hands to the deciding warp
 struct I4Result { int tried, mode_bits, cbp, bits; long long d; };
 
-__global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
+__device__ __forceinline__ void i4_pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }   // the two Intra4x4 warps
+
+__global__ void __launch_bounds__(96) k_intra_rows(FrameCtx f) {
   __shared__ __align__(16) MbTile t;
   __shared__ __align__(16) IntraNb nb;
   __shared__ __align__(16) I4State i4;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
   const int lm = lane >> 2, ly = lane & 3;                                    // candidate mode / row evaluated by this lane
   const int lm_need = (lm == 0 || lm == 3 || lm == 7) ? 0 : lm == 1 ? 1 : lm == 2 ? 2 : 3;   // needs: above / left / nothing / all three
   if (threadIdx.x < 4) nb.left_modes[threadIdx.x] = 2;
-  for (int i = threadIdx.x; i < 144; i += 64) (&i4.code[0][0])[i] = (&i4_pred_code[0][0])[i];
+  for (int i = threadIdx.x; i < 144; i += 96) (&i4.code[0][0])[i] = (&i4_pred_code[0][0])[i];
   __syncthreads();
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(&i4.code[lm][ly * 4]);   // V-indices of this lane's four predicted samples
   const uint32_t ch = *reinterpret_cast<const uint32_t*>(&i4.code[8][ly * 4]);    // ... for horizontal-up
@@ -254,7 +257,11 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
       d16 = __reduce_add_sync(FULL, s);
     }
     } else {
-    // ================= warp 1: Intra4x4 candidate ===========================================================
+    // ================= warps 1 and 2: Intra4x4 candidate ====================================================
+    // The 16 blocks form a wavefront (a block needs its left, above, above-left and above-right neighbours): at step
+    // T = bx + 2*by at most two blocks are ready, so the pair of warps finishes the macroblock in 10 steps instead of 16.
+    const int u = warp - 1;
+    uint8_t* const V = i4.v[u];
     const int best_key = i16_decide(nb, t, lane, has_top, has_left).key;      // same decision as warp 0 (reads only)
     // ---- Intra4x4 candidate: 16 blocks in decoding order ----------------------------------------------
     // rt = reconstruction with a one-sample frame: rt[y+1][x+1] is macroblock sample (x,y), row 0 / column 0 hold the
@@ -263,12 +270,18 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
     int mode_bits4 = 0, cbp4 = 0, bits4_cavlc = 0;
     long long d4 = 0;
     if (try_i4) {
-      if (lane < 20) i4.rt[0][1 + lane] = nb.top_y[lane];
-      if (lane < 16) i4.rt[1 + lane][0] = nb.left_y[lane];
-      if (lane == 31) i4.rt[0][0] = (uint8_t)nb.tl_y;
-      __syncwarp();
-      for (int blk = 0; blk < 16; blk++) {
-        const int bx = ((blk >> 2) & 1) * 2 + (blk & 1), by = (blk >> 3) * 2 + ((blk >> 1) & 1);
+      if (u == 0) {
+        if (lane < 20) i4.rt[0][1 + lane] = nb.top_y[lane];
+        if (lane < 16) i4.rt[1 + lane][0] = nb.left_y[lane];
+        if (lane == 31) i4.rt[0][0] = (uint8_t)nb.tl_y;
+      }
+      i4_pair_barrier();
+      for (int T = 0; T < 10; T++) {
+        // raster position of this warp's block at step T (nibble-packed): warp u=0 takes row 0 and columns 2,3; u=1 columns 0,1 of rows 1..3
+        const int rp = u == 0 ? (int)((0xFEBA763210ull >> (4 * T)) & 15ull) : (T >= 2 && T <= 7 ? (int)((0xDC985400u >> (4 * T)) & 15u) : -1);
+        if (rp >= 0) {
+        const int bx = rp & 3, by = rp >> 2;
+        const int blk = (by >> 1) * 8 + (bx >> 1) * 4 + (by & 1) * 2 + (bx & 1);          // blkIdx in decoding order
         const bool has_a = bx > 0 || has_left, has_b = by > 0 || has_top;
         const bool has_d = (bx > 0 && by > 0) ? true : bx > 0 ? has_top : by > 0 ? has_left : (has_left && has_top);
         const int trc = (int)((0x111511eau >> (2 * (by * 4 + bx))) & 3u);      // 2-bit codes of i4_tr_inside, raster order
@@ -277,14 +290,14 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
           int row = by * 4, col = bx * 4;
           if (lane < 5) row += (lane == 0 ? 3 : 4 - lane) + 1;
           else if (lane > 5) { int j = lane == 14 ? 7 : lane - 6; if (j >= 4 && !has_c) j = 3; col += 1 + j; }   // 8.3.1.2: repeat p[3,-1]
-          i4.v[lane] = i4.rt[row][col];
+          V[lane] = i4.rt[row][col];
         }
         __syncwarp();
-        if (lane < 14) i4.v[16 + lane] = (uint8_t)f2(i4.v[lane], i4.v[lane + 1]);
-        else if (lane >= 16 && lane < 29) { const int i = lane - 15; i4.v[32 + i] = (uint8_t)f3(i4.v[i - 1], i4.v[i], i4.v[i + 1]); }
+        if (lane < 14) V[16 + lane] = (uint8_t)f2(V[lane], V[lane + 1]);
+        else if (lane >= 16 && lane < 29) { const int i = lane - 15; V[32 + i] = (uint8_t)f3(V[i - 1], V[i], V[i + 1]); }
         else if (lane == 31) {
-          const int st = i4.v[6] + i4.v[7] + i4.v[8] + i4.v[9], sl = i4.v[1] + i4.v[2] + i4.v[3] + i4.v[4];
-          i4.v[48] = (uint8_t)(has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128);
+          const int st = V[6] + V[7] + V[8] + V[9], sl = V[1] + V[2] + V[3] + V[4];
+          V[48] = (uint8_t)(has_a && has_b ? (st + sl + 4) >> 3 : has_b ? (st + 2) >> 2 : has_a ? (sl + 2) >> 2 : 128);
         }
         __syncwarp();
         // predicted mode (8.3.1.1)
@@ -296,8 +309,8 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
         }
         // modes 0..7: lane = mode*4 + row; mode 8: every group of four lanes evaluates it as well
         const uint32_t crow = *reinterpret_cast<const uint32_t*>(&t.cur_y[by * 4 + ly][bx * 4]);
-        const uint32_t pm4 = (uint32_t)i4.v[cm & 255] | ((uint32_t)i4.v[(cm >> 8) & 255] << 8) | ((uint32_t)i4.v[(cm >> 16) & 255] << 16) | ((uint32_t)i4.v[cm >> 24] << 24);
-        const uint32_t p84 = (uint32_t)i4.v[ch & 255] | ((uint32_t)i4.v[(ch >> 8) & 255] << 8) | ((uint32_t)i4.v[(ch >> 16) & 255] << 16) | ((uint32_t)i4.v[ch >> 24] << 24);
+        const uint32_t pm4 = (uint32_t)V[cm & 255] | ((uint32_t)V[(cm >> 8) & 255] << 8) | ((uint32_t)V[(cm >> 16) & 255] << 16) | ((uint32_t)V[cm >> 24] << 24);
+        const uint32_t p84 = (uint32_t)V[ch & 255] | ((uint32_t)V[(ch >> 8) & 255] << 8) | ((uint32_t)V[(ch >> 16) & 255] << 16) | ((uint32_t)V[ch >> 24] << 24);
         int sad_m = (int)__vsadu4(crow, pm4), sad_hu = (int)__vsadu4(crow, p84);
         sad_m += __shfl_xor_sync(FULL, sad_m, 1); sad_hu += __shfl_xor_sync(FULL, sad_hu, 1);
         sad_m += __shfl_xor_sync(FULL, sad_m, 2); sad_hu += __shfl_xor_sync(FULL, sad_hu, 2);
@@ -309,7 +322,7 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
         const int mode = key & 15;
         mode_bits4 += mode == pm ? 1 : 4;
         // lanes 0..15: one sample each; transform / quantise / reconstruct with shuffles (lanes 16..31 mirror 0..15)
-        const int pred = i4.v[i4.code[mode][rpos]];
+        const int pred = V[i4.code[mode][rpos]];
         const int res = (int)t.cur_y[by * 4 + py][bx * 4 + px] - pred;
         int v = fwd1(px, __shfl_sync(FULL, res, rowb), __shfl_sync(FULL, res, rowb + 1), __shfl_sync(FULL, res, rowb + 2), __shfl_sync(FULL, res, rowb + 3));
         v = fwd1(py, __shfl_sync(FULL, v, colb), __shfl_sync(FULL, v, colb + 4), __shfl_sync(FULL, v, colb + 8), __shfl_sync(FULL, v, colb + 12));
@@ -321,8 +334,12 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
         d = inv1(py, __shfl_sync(FULL, d, colb), __shfl_sync(FULL, d, colb + 4), __shfl_sync(FULL, d, colb + 8), __shfl_sync(FULL, d, colb + 12));
         if (lane < 16) i4.rt[by * 4 + py + 1][bx * 4 + px + 1] = (uint8_t)clip255(pred + ((d + 32) >> 6));
         if (lane == 0) { i4.modes[by * 4 + bx] = (uint8_t)mode; i4.nnz[by * 4 + bx] = (uint8_t)__popc(nzm); }
-        __syncwarp();
+        }
+        if (T == 9 && u == 1 && lane == 0) i4.mode_bits_part = mode_bits4;
+        i4_pair_barrier();
       }
+      if (u == 0) {
+      mode_bits4 += i4.mode_bits_part;
       // I4 luma size + distortion
 #pragma unroll
       for (int b = 0; b < 16; b++) if (i4.nnz[(((b >> 3) * 2 + ((b >> 1) & 1)) * 4) + ((b >> 2) & 1) * 2 + (b & 1)]) cbp4 |= 1 << (b >> 2);
@@ -337,8 +354,9 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
         for (int j = 0; j < 8; j++) { const int e = (int)t.cur_y[r8][c8 + j] - (int)i4.rt[r8 + 1][c8 + j + 1]; sd += e * e; }
         d4 = __reduce_add_sync(FULL, sd);
       }
+      }
     }
-    if (lane == 0) { r4.tried = try_i4; r4.mode_bits = mode_bits4; r4.cbp = cbp4; r4.bits = bits4_cavlc; r4.d = d4; }
+    if (u == 0 && lane == 0) { r4.tried = try_i4; r4.mode_bits = mode_bits4; r4.cbp = cbp4; r4.bits = bits4_cavlc; r4.d = d4; }
     }
     __syncthreads();
     // ================= decision, commit and write-out (warp 0) ============================================
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(64) k_intra_rows(FrameCtx f) {
 
 int launch_intra(const FrameCtx& f, cudaStream_t st) {
   cudaMemsetAsync(f.progress, 0, sizeof(int) * f.mbh, st);
-  k_intra_rows<<<f.mbh, 64, 0, st>>>(f);
+  k_intra_rows<<<f.mbh, 96, 0, st>>>(f);
   return 1;
 }
 
