@@ -1048,7 +1048,9 @@ static void rc_update(enc_t* e, int64_t bits, int64_t target, int idr) {
   e->rc_fullness += bits - target;
   if (e->rc_fullness < -4 * target) e->rc_fullness = -4 * target;
   if (e->rc_fullness > 16 * target) e->rc_fullness = 16 * target;
-  if (e->rc_fullness > 4 * target && dq < 1) dq = 1;
+  /* bucket over-full (typically after a key frame): raise the QP — unless this picture used under a quarter of its budget
+   * (static scene: the debt is being repaid anyway, a coarser QP would only blur it); then at most one step finer per picture */
+  if (e->rc_fullness > 4 * target) { if (r > 4) { if (dq < 1) dq = 1; } else if (dq < -1) dq = -1; }
   if (e->rc_fullness < -2 * target && dq > -1) dq = -1;
   e->rc_qp = clip3(10, 48, e->rc_qp + dq);
 }

@@ -405,7 +405,9 @@ __device__ __forceinline__ void rc_update_dev(RcState* rc, long long bits, long 
   long long full = rc->fullness + bits - target;
   if (full < -4 * target) full = -4 * target;
   if (full > 16 * target) full = 16 * target;
-  if (full > 4 * target && dq < 1) dq = 1;
+  // bucket over-full (typically after a key frame): raise the QP — unless this picture used under a quarter of its budget
+  // (static scene: the debt is being repaid anyway); then at most one step finer per picture
+  if (full > 4 * target) { if (r > 4) { if (dq < 1) dq = 1; } else if (dq < -1) dq = -1; }
   if (full < -2 * target && dq > -1) dq = -1;
   rc->fullness = full;
   rc->qp = clip3i(10, 48, qp_used + dq);

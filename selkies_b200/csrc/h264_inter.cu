@@ -111,29 +111,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
       const uint2 w = *reinterpret_cast<const uint2*>(f.cur + ysz + (size_t)(mby * 8 + r8) * f.cw + x0 + c8);
       *reinterpret_cast<uint2*>(&t.cur_uv[r8][c8]) = w;
     }
-    const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
-    if (x_inside) {   // 576 words = 18 per lane: issue every load before the first shared-memory store
-      uint32_t v[18];
-      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref_y + x0 - 16);
+    // the co-located 16x16 block first (window rows 16..31, words 4..7): most macroblocks of a desktop picture end here
 #pragma unroll
-      for (int k = 0; k < 18; k++) {
-        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        v[k] = __ldg(base + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * (f.cw >> 2) + w);
-      }
-#pragma unroll
-      for (int k = 0; k < 18; k++) {
-        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        sm.win[row][w] = v[k];
-      }
-    } else {   // picture edge: per-sample clamping (8.4.2.2.1 reference sample padding)
-      for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
-        const int row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        const uint8_t* rr = ref_y + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * f.cw;
-        uint32_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rr + clip3i(0, f.cw - 1, x0 - 16 + w * 4 + k)) << (8 * k);
-        sm.win[row][w] = v;
-      }
+    for (int k = 0; k < 2; k++) {
+      const int i = lane + 32 * k;
+      sm.win[16 + (i >> 2)][4 + (i & 3)] = __ldg(reinterpret_cast<const uint32_t*>(ref_y + (size_t)(y0 + (i >> 2)) * f.cw + x0) + (i & 3));
     }
   }
   __syncwarp();
@@ -148,6 +130,36 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
                                 sad4acc(*reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]), w0p[1], 0u));
     sad0 = __reduce_add_sync(FULL, (int)s0);
     if (sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda) best = 0xffffffffu;
+  }
+  if (best == 0xffffffffu) {   // not static: stage the rest of the 48x48 search window
+    const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
+    if (x_inside) {   // 512 more words = 16 per lane (of 18 slots): issue every load before the first shared-memory store
+      uint32_t v[18];
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref_y + x0 - 16);
+#pragma unroll
+      for (int k = 0; k < 18; k++) {
+        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        const bool centre = row >= 16 && row < 32 && w >= 4 && w < 8;
+        v[k] = centre ? 0u : __ldg(base + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * (f.cw >> 2) + w);
+      }
+#pragma unroll
+      for (int k = 0; k < 18; k++) {
+        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        const bool centre = row >= 16 && row < 32 && w >= 4 && w < 8;
+        if (!centre) sm.win[row][w] = v[k];
+      }
+    } else {   // picture edge: per-sample clamping (8.4.2.2.1 reference sample padding)
+      for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
+        const int row = i / WIN_WORDS, w = i - row * WIN_WORDS;
+        if (row >= 16 && row < 32 && w >= 4 && w < 8) continue;
+        const uint8_t* rr = ref_y + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * f.cw;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(rr + clip3i(0, f.cw - 1, x0 - 16 + w * 4 + k)) << (8 * k);
+        sm.win[row][w] = v;
+      }
+    }
+    __syncwarp();
   }
   // ---- temporal-predictor early termination (oracle/h264_ref.c encode_inter_mb): the vector this macroblock
   // had in the previous picture, rounded to full samples (scrolling / panning content repeats it).  Accepted without the
