@@ -146,15 +146,16 @@ def csc_dram_traffic():
     encoder kernels that follow (write side: a few KB), so traffic < algorithmic bytes."""
     try:
         import csv, glob
-        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_v*_raw.csv")), key=lambda p: (len(p), p))
-        rows = list(csv.reader(open(files[-1])))
-        hdr, units = rows[0], rows[1]
-        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_v*_raw.csv")), key=lambda p: os.path.basename(p).split("_raw")[0][:len("r1_ncu_full_v9")])
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        for r in rows[2:]:
-            if "csc_bgra_nv12" in r[ik]:
-                rd, wr = float(r[ir]) * scale.get(units[ir], 1), float(r[iw]) * scale.get(units[iw], 1)
-                return rd + wr, rd, wr, os.path.basename(files[-1])
+        for path in reversed(files):              # newest capture that holds a CSC launch
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            for r in rows[2:]:
+                if "csc_bgra_nv12" in r[ik]:
+                    rd, wr = float(r[ir]) * scale.get(units[ir], 1), float(r[iw]) * scale.get(units[iw], 1)
+                    return rd + wr, rd, wr, os.path.basename(path)
     except Exception:
         pass
     return None, None, None, None
