@@ -16,22 +16,22 @@ RTP_VIDEO_CLOCK_RATE = 90000
 
 
 class PipelineBridge:
-    """Depth-1 drop-oldest bridge, same contract as rtc.py:102-118 (a lagging consumer sees the newest sample only)."""
+    """Newest-sample-wins mailbox between the encoder callback and the RTP sender: same contract as the reference's bridge
+    (rtc.py:102-118: a lagging consumer sees the newest sample only; `get_data` waits for one).  Everything happens on the
+    event loop and `set_data` never yields between the drop and the put, so no lock is involved."""
 
     def __init__(self):
-        self._lock = asyncio.Lock()
-        self._queue: asyncio.Queue = asyncio.Queue(maxsize=1)
+        self._slot: asyncio.Queue = asyncio.Queue(maxsize=1)
         self.dropped = 0
 
     async def set_data(self, data: Any):
-        async with self._lock:
-            if self._queue.full():
-                self._queue.get_nowait()
-                self.dropped += 1
-            self._queue.put_nowait(data)
+        while self._slot.full():
+            self._slot.get_nowait()
+            self.dropped += 1
+        self._slot.put_nowait(data)
 
     async def get_data(self):
-        return await self._queue.get()
+        return await self._slot.get()
 
 
 class VideoSample:
