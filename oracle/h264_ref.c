@@ -1164,7 +1164,7 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   { int coded = 0; for (int i = 0; i < mbs; i++) coded |= !skip_copy[i]; int painted = rc_mode == 1 && e->paint_trigger > 0 && !idr && e->static_run == e->paint_trigger;
     e->static_run = painted ? e->paint_trigger + 1 : (coded || idr) ? 0 : e->static_run + 1; free(skip_copy); }
   e->last_qp = qp; e->last_bits = (int64_t)o * 8;
-  if (rc_mode == 0) rc_update(e, (int64_t)o * 8, target_bits, idr);
+  if (rc_mode == 0) rc_update(e, bits, target_bits, idr);      /* RBSP bits of the slices: known before the byte stream is assembled */
   if (idr) e->idr_count++;
   e->frame_num = (e->frame_num + 1) & 255;
   return (int64_t)o;

@@ -51,7 +51,7 @@ struct Session {
   int device = 0, sm_count = 148;
   int src_w = 0, src_h = 0, dst_w = 0, dst_h = 0, coded_w = 0, coded_h = 0;
   bool encode = true, timing = false, timing_csc_only = false;
-  cudaStream_t st_copy = nullptr, st_enc = nullptr, st_out = nullptr;
+  cudaStream_t st_copy = nullptr, st_enc = nullptr, st_out = nullptr, st_pack = nullptr;
 
   // ingest ring
   int n_slots = 4;
@@ -339,8 +339,9 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
   CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
   if (s->encode) {
     fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = s->timing_csc_only ? nullptr : ev; fp.csc_ts = cp.ts;
+    fp.st_pack = fp.ev ? nullptr : s->st_pack;      // per-stage events need the serial schedule
     nl += encoder_encode(s->enc, &fp, s->st_enc);
-    CK(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
+    CK(cudaEventRecord(s->ev_enc[out_idx], fp.st_pack ? fp.st_pack : s->st_enc));      // the access unit is complete here
     CK(cudaStreamWaitEvent(s->st_out, s->ev_enc[out_idx], 0));
     size_t first = s->au_cap < kFirstChunk ? s->au_cap : kFirstChunk;
     CK(cudaMemcpyAsync(s->h_out[out_idx], s->d_au[out_idx], first, cudaMemcpyDeviceToHost, s->st_out));
@@ -375,6 +376,7 @@ void release_session(Session* s) {
   if (s->st_copy) cudaStreamDestroy(s->st_copy);
   if (s->st_enc) cudaStreamDestroy(s->st_enc);
   if (s->st_out) cudaStreamDestroy(s->st_out);
+  if (s->st_pack) cudaStreamDestroy(s->st_pack);
   delete s;
 }
 
@@ -423,6 +425,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&s->st_enc, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&s->st_pack, cudaStreamNonBlocking);
   for (int i = 0; i < kMaxSlots; i++) {
     cudaEventCreateWithFlags(&s->ev_h2d[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s->ev_csc[i], cudaEventDisableTiming);

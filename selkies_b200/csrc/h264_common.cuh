@@ -31,7 +31,8 @@ struct RcState {
   int32_t last_qp;
   int32_t frames;
   int32_t static_run;      // consecutive pictures in which every macroblock was skipped
-  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by the pack kernel
+  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by k_rc_update
+  long long pic_bits;      // RBSP bits of the picture just scanned (k_rc_update -> AuHeader.total_bits)
 };
 
 struct FrameCtx {          // everything a kernel needs about the picture being coded

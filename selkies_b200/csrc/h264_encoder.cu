@@ -36,6 +36,7 @@ struct Encoder {
   uint8_t* param_sets = nullptr; int param_len = 0, param_len_last = 0;
   int band_rows = 0, n_bands = 1, striped = 0, au_data_off = (int)sizeof(AuHeader);
   int *band_fn = nullptr, *band_coded = nullptr;
+  cudaEvent_t ev_scanned = nullptr, ev_packed = nullptr;   // two-stream schedule: scan+rc done on the main stream / AU packed on st_pack
   size_t au_cap = 0;
   int frame_num = 0, idr_count = 0;
   bool have_ref = false;
@@ -178,6 +179,8 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMemset(e->band_fn, 0, e->n_bands * sizeof(int)));
   ECK(cudaMalloc((void**)&e->band_coded, e->n_bands * sizeof(int)));
   ECK(cudaMemset(e->band_coded, 0, e->n_bands * sizeof(int)));
+  ECK(cudaEventCreateWithFlags(&e->ev_scanned, cudaEventDisableTiming));
+  ECK(cudaEventCreateWithFlags(&e->ev_packed, cudaEventDisableTiming));
   e->au_cap = (size_t)e->au_data_off + (size_t)e->n_bands * (e->param_len + e->param_len_last) + (size_t)e->n_slices * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
   *out = e;
   return 0;
@@ -188,6 +191,8 @@ void encoder_destroy(Encoder* e) {
   void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo, e->coef, e->nnz, e->mb_words, e->mb_nbits, e->slice_buf, e->slice_size,
                   e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes, e->band_fn, e->band_coded};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (e->ev_scanned) cudaEventDestroy(e->ev_scanned);
+  if (e->ev_packed) cudaEventDestroy(e->ev_packed);
   delete e;
 }
 
@@ -215,12 +220,26 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   int n = 0;
   n += idr ? launch_intra(f, st) : launch_inter(f, st);
   if (p->ev) cudaEventRecord(p->ev[2], st);
+  // Two-stream schedule (no per-stage events requested): the byte-stream assembly of picture N (copy, emulation-prevention
+  // count, pack) runs on st_pack while st already analyses picture N+1.  What those kernels read is not written by the
+  // analysis kernels (bit strings, slice scratch, the reconstruction of N — a read-only reference for N+1); the entropy
+  // kernels of N+1, which do rewrite it, wait for ev_packed.  The rate controller has already advanced in k_rc_update.
+  const bool overlap = p->st_pack != nullptr && p->ev == nullptr;
+  if (overlap) cudaStreamWaitEvent(st, e->ev_packed, 0);          // the previous picture's pack (no-op before the first)
   n += launch_cavlc(f, st);
   if (p->ev) cudaEventRecord(p->ev[3], st);
-  n += launch_slice(f, st);
+  n += launch_slice_scan(f, st);
+  cudaStream_t sp = st;
+  if (overlap) {
+    sp = p->st_pack;
+    cudaEventRecord(e->ev_scanned, st);
+    cudaStreamWaitEvent(sp, e->ev_scanned, 0);
+  }
+  n += launch_slice_copy_ep(f, sp);
   if (p->ev) cudaEventRecord(p->ev[4], st);
-  n += launch_pack_cap(f, (long long)e->au_cap, st);
+  n += launch_pack_cap(f, (long long)e->au_cap, sp);
   if (p->ev) cudaEventRecord(p->ev[5], st);
+  if (overlap) cudaEventRecord(e->ev_packed, sp);
   if (idr) e->idr_count++;
   e->frame_num = (e->frame_num + 1) & 255;
   e->have_ref = true;

@@ -43,7 +43,9 @@ struct EncodeFrameParams {
   int qp_fixed;
   int paint_trigger, paint_qp;   // CQP paint-over (0 = off)
   int64_t target_bits;     // per frame, CBR
-  cudaEvent_t* ev;         // null, or 8 timing events: encoder records ev[2..5] after each stage
+  cudaEvent_t* ev;         // null, or 8 timing events: encoder records ev[2..5] after each stage (forces the serial schedule)
+  cudaStream_t st_pack;    // null = everything on `st`; else the byte-stream assembly of this picture (k_slice_copy/ep, k_pack_au)
+                           // runs here, overlapping the analysis of the next picture on `st`.  The access unit is complete on st_pack.
   const unsigned long long* csc_ts;   // null, or the CSC launch's device stamps to forward in the AuHeader
 };
 
@@ -52,7 +54,7 @@ void encoder_destroy(Encoder* e);
 size_t encoder_au_capacity(const Encoder* e);
 int  encoder_au_data_offset(const Encoder* e);   // AuHeader + band table (+ slack for an in-place stripe header)
 int  encoder_band_count(const Encoder* e);       // 0 when full-frame
-// enqueue one frame on `st`; returns the number of kernel launches issued
+// enqueue one frame on `st` (and `p->st_pack`); returns the number of kernel launches issued
 int  encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st);
 const uint8_t* encoder_recon(const Encoder* e);   // NV12 reconstruction of the last encoded frame
 const char* encoder_last_error();

@@ -418,7 +418,9 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
   __shared__ int s_wsum[PACK_THREADS / 32];
   __shared__ int s_carry;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int qp = frame_qp(f);
+  // the controller has already moved on to the next picture (k_rc_update runs before this kernel, possibly on another
+  // stream): this picture's QP is the one it recorded
+  const int qp = f.rc->last_qp;
   // byte offset of this slice's NAL inside the access unit
   long long part = 0;
   for (int j = tid; j < s; j += PACK_THREADS) part += f.slice_size[j];
@@ -519,17 +521,8 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
       if (total > cap) { ovf |= 2; total = cap; }
       h->size = (int32_t)total; h->qp = qp; h->is_idr = f.idr; h->n_slices = f.n_slices; h->total_bits = bits;
       h->overflow = ovf;
-      // the controller evolves the running QP, not the (possibly raised) QP this picture was coded with
-      const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
-      if (f.rc_mode == 0) rc_update_dev(f.rc, total * 8, f.target_bits, f.idr, run_qp);
       h->next_qp = f.rc->qp;
       h->csc_t0 = f.csc_ts ? f.csc_ts[0] : 0; h->csc_t1 = f.csc_ts ? f.csc_ts[1] : 0;
-      f.rc->last_qp = qp; f.rc->frames++;
-      const int coded = f.rc->pic_coded;
-      f.rc->pic_coded = 0;
-      // a paint-over picture parks the counter above the trigger, so the scene is refined once until something moves again
-      const bool painted = f.rc_mode == 1 && f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger;
-      f.rc->static_run = painted ? f.paint_trigger + 1 : (coded || f.idr) ? 0 : f.rc->static_run + 1;
     }
   }
 }
@@ -539,12 +532,39 @@ int launch_cavlc(const FrameCtx& f, cudaStream_t st) {
   k_cavlc_mb<<<(mbs + CAVLC_WARPS - 1) / CAVLC_WARPS, 32 * CAVLC_WARPS, 0, st>>>(f);
   return 1;
 }
-int launch_slice(const FrameCtx& f, cudaStream_t st) {
-  const int mbs = f.mbw * f.mbh;
+// ---- k_rc_update: one warp, right after the slice scan.  The picture's RBSP bit count is known at that point (the byte
+// stream adds start codes and emulation prevention, which the controller does not need), so the rate controller, the
+// paint-over counter and the per-picture flags advance HERE and the next picture's analysis can start while this picture's
+// byte stream is still being assembled (k_slice_copy / k_slice_ep / k_pack_au on the packing stream).
+__global__ void __launch_bounds__(32) k_rc_update(FrameCtx f) {
+  const int lane = threadIdx.x;
+  const int qp = frame_qp(f);                         // QP this picture was coded with (state before the update)
+  long long bits = 0;
+  for (int j = lane; j < f.n_slices; j += 32) bits += f.slice_bits[j];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
+  if (lane != 0) return;
+  // the controller evolves the running QP, not the (possibly raised) QP this picture was coded with
+  const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
+  if (f.rc_mode == 0) rc_update_dev(f.rc, bits, f.target_bits, f.idr, run_qp);
+  f.rc->last_qp = qp; f.rc->frames++; f.rc->pic_bits = bits;
+  const int coded = f.rc->pic_coded;
+  f.rc->pic_coded = 0;
+  // a paint-over picture parks the counter above the trigger, so the scene is refined once until something moves again
+  const bool painted = f.rc_mode == 1 && f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger;
+  f.rc->static_run = painted ? f.paint_trigger + 1 : (coded || f.idr) ? 0 : f.rc->static_run + 1;
+}
+
+int launch_slice_scan(const FrameCtx& f, cudaStream_t st) {
   k_slice_scan<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
+  k_rc_update<<<1, 32, 0, st>>>(f);
+  return 2;
+}
+int launch_slice_copy_ep(const FrameCtx& f, cudaStream_t st) {
+  const int mbs = f.mbw * f.mbh;
   k_slice_copy<<<(mbs * COPY_LANES + COPY_THREADS - 1) / COPY_THREADS, COPY_THREADS, 0, st>>>(f);
   k_slice_ep<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
-  return 3;
+  return 2;
 }
 int launch_pack_cap(const FrameCtx& f, long long au_cap, cudaStream_t st) {
   k_pack_au<<<f.n_slices, PACK_THREADS, 0, st>>>(f, au_cap);
