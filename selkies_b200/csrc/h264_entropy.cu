@@ -227,6 +227,38 @@ __device__ __forceinline__ void or_word(uint32_t* out, long long bitpos, uint32_
   else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
 }
 
+__device__ __forceinline__ void rc_update_dev(RcState* rc, long long bits, long long target, int idr, int qp_used) {
+  if (target < 1) target = 1;
+  const long long ref = idr ? 4 * target : target;
+  const long long r = bits * 16 / ref;
+  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 1 ? -4 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
+  long long full = rc->fullness + bits - target;
+  if (full < -4 * target) full = -4 * target;
+  if (full > 16 * target) full = 16 * target;
+  // bucket over-full (typically after a key frame): raise the QP — unless this picture used under a quarter of its budget
+  // (static scene: the debt is being repaid anyway); then at most one step finer per picture
+  if (full > 4 * target) { if (r > 4) { if (dq < 1) dq = 1; } else if (dq < -1) dq = -1; }
+  if (full < -2 * target && dq > -1) dq = -1;
+  rc->fullness = full;
+  rc->qp = clip3i(10, 48, qp_used + dq);
+}
+
+// ---- rate-control step, run by the LAST slice-scan block of the picture (thread 0).  The picture's RBSP bit count is known
+// at that point (the byte stream adds start codes and emulation prevention, which the controller does not need), so the rate
+// controller, the paint-over counter and the per-picture flags advance here and the next picture's analysis can start while
+// this picture's byte stream is still being assembled (k_slice_copy / k_slice_ep / k_pack_au on the packing stream).
+__device__ __forceinline__ void rc_step(const FrameCtx& f, int qp, long long bits) {
+  // the controller evolves the running QP, not the (possibly raised) QP this picture was coded with
+  const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
+  if (f.rc_mode == 0) rc_update_dev(f.rc, bits, f.target_bits, f.idr, run_qp);
+  f.rc->last_qp = qp; f.rc->frames++; f.rc->pic_bits = bits;
+  const int coded = __ldcg(&f.rc->pic_coded);      // stored by other blocks of this launch: read through L2
+  f.rc->pic_coded = 0;
+  // a paint-over picture parks the counter above the trigger, so the scene is refined once until something moves again
+  const bool painted = f.rc_mode == 1 && f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger;
+  f.rc->static_run = painted ? f.paint_trigger + 1 : (coded || f.idr) ? 0 : f.rc->static_run + 1;
+}
+
 // ---- k_slice_scan: one block per slice.  Block-wide scans give every macroblock (a) its mb_skip_run and (b) the bit
 // offset of its first bit inside the slice RBSP.  Nothing is copied here, so a slice of many macroblock rows costs one
 // short loop iteration per 256 macroblocks.
@@ -234,6 +266,7 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
   __shared__ long long s_warp_sum[SLICE_THREADS / 32];
   __shared__ int s_warp_max[SLICE_THREADS / 32];
   __shared__ long long s_carry_bits;
+  __shared__ bool s_is_last;
   __shared__ int s_carry_last;      // index (within the slice) of the last non-skipped macroblock seen so far
   __shared__ uint32_t s_nb[SLICE_THREADS];
   __shared__ int s_run[SLICE_THREADS];
@@ -318,6 +351,26 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
     }
     g.put(1, 1);
     f.slice_rbsp[s] = (uint32_t)((g.pos + 7) >> 3);
+    // last block of the picture to get here runs the rate-control step (every block read its QP from the controller at its
+    // start, i.e. before this point, so the update cannot disturb a block still running)
+    __threadfence();
+    s_is_last = atomicAdd(&f.rc->scan_done, 1) == f.n_slices - 1;
+  }
+  __syncthreads();
+  if (s_is_last) {
+    __threadfence();
+    long long bits = 0;
+    for (int j = tid; j < f.n_slices; j += SLICE_THREADS) bits += __ldcg(&f.slice_bits[j]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
+    if (lane == 0) s_warp_sum[warp] = bits;
+    __syncthreads();
+    if (tid == 0) {
+      long long t = 0;
+      for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_warp_sum[w];
+      f.rc->scan_done = 0;
+      rc_step(f, qp, t);
+    }
   }
 }
 
@@ -396,22 +449,6 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_ep(FrameCtx f) {
 // ------------------------------------------------------------------------------------------------ k_pack_au
 constexpr int PACK_THREADS = 256;
 constexpr int PACK_CH = 16;      // bytes per thread per round
-
-__device__ __forceinline__ void rc_update_dev(RcState* rc, long long bits, long long target, int idr, int qp_used) {
-  if (target < 1) target = 1;
-  const long long ref = idr ? 4 * target : target;
-  const long long r = bits * 16 / ref;
-  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 1 ? -4 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
-  long long full = rc->fullness + bits - target;
-  if (full < -4 * target) full = -4 * target;
-  if (full > 16 * target) full = 16 * target;
-  // bucket over-full (typically after a key frame): raise the QP — unless this picture used under a quarter of its budget
-  // (static scene: the debt is being repaid anyway); then at most one step finer per picture
-  if (full > 4 * target) { if (r > 4) { if (dq < 1) dq = 1; } else if (dq < -1) dq = -1; }
-  if (full < -2 * target && dq > -1) dq = -1;
-  rc->fullness = full;
-  rc->qp = clip3i(10, 48, qp_used + dq);
-}
 
 __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long au_cap) {
   __shared__ long long s_base;
@@ -532,33 +569,9 @@ int launch_cavlc(const FrameCtx& f, cudaStream_t st) {
   k_cavlc_mb<<<(mbs + CAVLC_WARPS - 1) / CAVLC_WARPS, 32 * CAVLC_WARPS, 0, st>>>(f);
   return 1;
 }
-// ---- k_rc_update: one warp, right after the slice scan.  The picture's RBSP bit count is known at that point (the byte
-// stream adds start codes and emulation prevention, which the controller does not need), so the rate controller, the
-// paint-over counter and the per-picture flags advance HERE and the next picture's analysis can start while this picture's
-// byte stream is still being assembled (k_slice_copy / k_slice_ep / k_pack_au on the packing stream).
-__global__ void __launch_bounds__(32) k_rc_update(FrameCtx f) {
-  const int lane = threadIdx.x;
-  const int qp = frame_qp(f);                         // QP this picture was coded with (state before the update)
-  long long bits = 0;
-  for (int j = lane; j < f.n_slices; j += 32) bits += f.slice_bits[j];
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
-  if (lane != 0) return;
-  // the controller evolves the running QP, not the (possibly raised) QP this picture was coded with
-  const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
-  if (f.rc_mode == 0) rc_update_dev(f.rc, bits, f.target_bits, f.idr, run_qp);
-  f.rc->last_qp = qp; f.rc->frames++; f.rc->pic_bits = bits;
-  const int coded = f.rc->pic_coded;
-  f.rc->pic_coded = 0;
-  // a paint-over picture parks the counter above the trigger, so the scene is refined once until something moves again
-  const bool painted = f.rc_mode == 1 && f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger;
-  f.rc->static_run = painted ? f.paint_trigger + 1 : (coded || f.idr) ? 0 : f.rc->static_run + 1;
-}
-
 int launch_slice_scan(const FrameCtx& f, cudaStream_t st) {
   k_slice_scan<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
-  k_rc_update<<<1, 32, 0, st>>>(f);
-  return 2;
+  return 1;
 }
 int launch_slice_copy_ep(const FrameCtx& f, cudaStream_t st) {
   const int mbs = f.mbw * f.mbh;
