@@ -31,7 +31,7 @@ struct RcState {
   int32_t last_qp;
   int32_t frames;
   int32_t static_run;      // consecutive pictures in which every macroblock was skipped
-  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by k_rc_update
+  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by rc_step (last slice-scan block)
   long long pic_bits;      // RBSP bits of the picture just scanned (rate-control step -> AuHeader.total_bits)
   int32_t scan_done;       // slice-scan blocks that have finished this picture (the last one runs the rate-control step)
   int32_t pad3;

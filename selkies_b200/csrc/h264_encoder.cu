@@ -223,7 +223,7 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   // Two-stream schedule (no per-stage events requested): the byte-stream assembly of picture N (copy, emulation-prevention
   // count, pack) runs on st_pack while st already analyses picture N+1.  What those kernels read is not written by the
   // analysis kernels (bit strings, slice scratch, the reconstruction of N — a read-only reference for N+1); the entropy
-  // kernels of N+1, which do rewrite it, wait for ev_packed.  The rate controller has already advanced in k_rc_update.
+  // kernels of N+1, which do rewrite it, wait for ev_packed.  The rate controller has already advanced in k_slice_scan (rc_step).
   const bool overlap = p->st_pack != nullptr && p->ev == nullptr;
   if (overlap) cudaStreamWaitEvent(st, e->ev_packed, 0);          // the previous picture's pack (no-op before the first)
   n += launch_cavlc(f, st);

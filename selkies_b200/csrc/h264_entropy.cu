@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
   __shared__ int s_wsum[PACK_THREADS / 32];
   __shared__ int s_carry;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // the controller has already moved on to the next picture (k_rc_update runs before this kernel, possibly on another
+  // the controller has already moved on to the next picture (rc_step ran in k_slice_scan, before this kernel and possibly on another
   // stream): this picture's QP is the one it recorded
   const int qp = f.rc->last_qp;
   // byte offset of this slice's NAL inside the access unit
