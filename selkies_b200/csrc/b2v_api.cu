@@ -5,9 +5,11 @@
 // selkies.py:3091-3189): start_capture -> b2v_create, stop_capture -> b2v_destroy,
 // update_framerate / update_video_bitrate / request_idr_frame -> b2v_set_* / b2v_request_idr.
 //
-// Per-frame flow (three streams, events in between; nothing on the host blocks except ring back-pressure):
+// Per-frame flow (four streams, events in between; nothing on the host blocks except ring back-pressure):
 //   st_copy : cudaMemcpyAsync  pinned slot -> device BGRA slot                      (a) ingest
-//   st_enc  : fused CSC(+scale) -> NV12 cur ; H.264 encode kernels -> AU in HBM      (b),(c)
+//   st_enc  : fused CSC(+scale) -> NV12 cur ; analysis, CAVLC, slice scan + rate control       (b),(c)
+//   st_pack : byte-stream assembly of the same picture (slice copy, EP count, pack) -> AU in HBM,
+//             overlapping the next picture on st_enc (h264_encoder.cu)
 //   st_out  : cudaMemcpyAsync  AU head (size + first chunk) -> pinned output slot
 //   output thread: waits the D2H event, fetches the tail of oversized AUs, runs the callback in order.
 #include <condition_variable>
