@@ -138,3 +138,46 @@ def test_screen_capture_striped_mode():
     for y0, st in by_y.items():
         Y, _, _ = avdec.decode_stream(st, quiet=True)[-1]
         assert Y.shape == (min(h, y0 + 64) - y0, w)
+
+
+def test_ws_video_channel_carries_stripes_from_the_native_thread():
+    """ScreenCapture (striped) -> WsVideoChannel.on_stripe on the native output thread -> sender task -> per-stripe decoders."""
+    import asyncio
+    from selkies_b200.pixelflux_compat import ArraySource, CaptureSettings, ScreenCapture, StripeCallback
+    from selkies_b200.ws_video import WsVideoChannel
+    w, h = 320, 200
+    frames = frames_with_static_top(w, h, 6)
+
+    async def run():
+        loop = asyncio.get_running_loop()
+        sent = []
+
+        async def send(b):
+            sent.append(b)
+        ch = WsVideoChannel(send, loop, queue_depth=256, fps=120.0)
+        sender = asyncio.ensure_future(ch.run_sender())
+        cs = CaptureSettings()
+        cs.capture_width, cs.capture_height, cs.target_fps = w, h, 120.0
+        cs.h264_fullframe, cs.h264_crf, cs.h264_stripe_rows = False, 28, 4
+        cap = ScreenCapture(ArraySource(frames, loop=False))
+        await loop.run_in_executor(None, cap.start_capture, cs, StripeCallback(ch.on_stripe))
+        for _ in range(400):
+            await asyncio.sleep(0.01)
+            if ch.last_sent_id >= 5 and ch.queue.empty():
+                break
+        await loop.run_in_executor(None, cap.stop_capture)
+        await asyncio.sleep(0.05)
+        await ch.queue.join()
+        sender.cancel()
+        ch.on_ack(f"CLIENT_FRAME_ACK {ch.last_sent_id}")
+        assert ch.evaluate_gate() and ch.dropped == 0
+        return sent
+    sent = asyncio.run(run())
+    by_y = {}
+    for d in sent:
+        assert d[0] == 0x04
+        by_y.setdefault(int.from_bytes(d[4:6], "big"), []).append(d[10:])
+    assert sorted(by_y) == [0, 64, 128, 192] and len(by_y[0]) == 1
+    for y0, st in by_y.items():
+        Y, _, _ = avdec.decode_stream(st, quiet=True)[-1]
+        assert Y.shape == (min(h, y0 + 64) - y0, w)
