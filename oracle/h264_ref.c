@@ -110,6 +110,7 @@ typedef struct {
   int stripe_fn[MAX_STRIPES];
   int32_t stripe_tab[MAX_STRIPES][3];   /* last picture: byte offset, size, coded flag */
   uint8_t sps_band[2][64]; int sps_band_len[2];   /* [0] regular band, [1] last band (may be shorter / cropped) */
+  int no_i4, no_tpred;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED, read once at create) */
 } enc_t;
 
 static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -569,7 +570,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
       for (int blk = 0; blk < 16; blk++) bits4 += m4.i4_modes[blk_y[blk] * 4 + blk_x[blk]] == i4_pred_mode(e, mbx, mby, blk_x[blk], blk_y[blk]) ? 1 : 4;
       *m = keep; }
     const int64_t l2 = rd_lambda[qp];
-    if (d4 + l2 * bits4 < d16 + l2 * bits16 && !getenv("B2V_REF_NO_I4")) {
+    if (d4 + l2 * bits4 < d16 + l2 * bits16 && !e->no_i4) {
       int8_t cm = m->chroma_mode;
       *m = m4; m->type = 3; m->chroma_mode = cm;
       for (int r = 0; r < 16; r++) memcpy(ry + (size_t)(mby * 16 + r) * e->cw + mbx * 16, rec4 + 16 * r, 16);
@@ -661,7 +662,7 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
    * AND it costs less than the zero vector (otherwise a stale vector could survive on a scene that has become static);
    * quarter-sample refinement then runs as after a search. */
   int pred_hit = 0;
-  if (search && prev_type == 1 && !getenv("B2V_REF_NO_TPRED")) {   /* the switch exists for A/B experiments only */
+  if (search && prev_type == 1 && !e->no_tpred) {
     const int cdx = asr(prev_mvx + 2, 2), cdy = asr(prev_mvy + 2, 2);
     if ((cdx || cdy) && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
       uint32_t kc = 0, kmin = 0xffffffffu;
@@ -1067,6 +1068,7 @@ void* b2v_ref_enc_create(int width, int height, int slice_rows) {
   e->recon[0] = (uint8_t*)calloc(fb, 1); e->recon[1] = (uint8_t*)calloc(fb, 1);
   e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
   e->rc_qp = -1;
+  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL;
   write_param_sets(e);
   return e;
 }
