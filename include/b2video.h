@@ -127,6 +127,9 @@ void b2v_destroy(void* h);                 /* blocks: drains frames, joins the o
  *      SURVEY.md §3.2 hot loop #1). ------------------------------------------ */
 void* b2v_ring_acquire(void* h, int32_t* slot);          /* blocks until a slot is free */
 int   b2v_ring_submit(void* h, int32_t slot, int32_t stride_bytes, int64_t capture_ns);
+/* Give an acquired slot back WITHOUT encoding it (the producer had no frame after all: end of a canned source, a grab that
+ * failed).  Only the most recently acquired slot can be returned; the next b2v_ring_acquire hands out the same slot. */
+int   b2v_ring_release(void* h, int32_t slot);
 /* device-resident frames (bench `value`: inputs already in HBM) */
 int   b2v_resident_upload(void* h, int32_t index, const void* bgra_host, int32_t stride_bytes);
 int   b2v_submit_resident(void* h, int32_t index, int64_t capture_ns);

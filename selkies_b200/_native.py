@@ -64,6 +64,7 @@ SYMBOLS = [
     ("b2v_destroy", None, [C.c_void_p]),
     ("b2v_ring_acquire", C.c_void_p, [C.c_void_p, C.POINTER(C.c_int32)]),
     ("b2v_ring_submit", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
+    ("b2v_ring_release", C.c_int, [C.c_void_p, C.c_int32]),
     ("b2v_resident_upload", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     ("b2v_submit_resident", C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     ("b2v_flush", C.c_int, [C.c_void_p]),

@@ -473,6 +473,19 @@ void* b2v_ring_acquire(void* h, int32_t* slot) {
   return s->host_slot[found];
 }
 
+int b2v_ring_release(void* h, int32_t slot) {
+  Session* s = (Session*)h;
+  if (!s || slot < 0 || slot >= s->n_slots) return fail(B2V_EINVAL, "bad slot");
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->slot_free[slot] || (slot + 1) % s->n_slots != s->ring_next) return fail(B2V_ESTATE, "slot %d is not the most recently acquired one", slot);
+    s->slot_free[slot] = true;
+    s->ring_next = slot;
+  }
+  s->cv_slot.notify_all();
+  return 0;
+}
+
 int b2v_ring_submit(void* h, int32_t slot, int32_t stride, int64_t capture_ns) {
   Session* s = (Session*)h;
   if (!s || slot < 0 || slot >= s->n_slots) return fail(B2V_EINVAL, "bad slot");

@@ -302,8 +302,7 @@ class ScreenCapture:
                 w, h = self._w, self._h_px
                 view = np.frombuffer((C.c_ubyte * (w * h * 4)).from_address(p), np.uint8).reshape(h, w, 4)
                 if not self._source.fill(view, index):
-                    # hand the slot back through an ordinary submit so the ring stays consistent, then stop
-                    self._lib.b2v_ring_submit(self._h, slot.value, w * 4, time.monotonic_ns())
+                    self._lib.b2v_ring_release(self._h, slot.value)      # end of the source: nothing to encode
                     break
                 N.check(self._lib.b2v_ring_submit(self._h, slot.value, w * 4, time.monotonic_ns()))
                 fps = self._fps

@@ -81,6 +81,10 @@ class Session:
         buf = (C.c_ubyte * (self.width * self.height * 4)).from_address(p)
         return slot.value, np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 4)
 
+    def release_slot(self, slot: int) -> None:
+        """Give the most recently acquired slot back without encoding it."""
+        N.check(self._lib.b2v_ring_release(self._h, slot))
+
     def submit_slot(self, slot: int, capture_ns: int = 0) -> None:
         N.check(self._lib.b2v_ring_submit(self._h, slot, self.width * 4, capture_ns))
 

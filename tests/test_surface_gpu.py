@@ -12,6 +12,8 @@ from oracle import avdec
 from selkies_b200.gst_webrtc_app import GSTWebRTCApp, GSTWebRTCAppError
 from selkies_b200.media_pipeline import MediaPipelineB200, RateControlMode
 from selkies_b200.pixelflux_compat import ArraySource, CaptureSettings, ScreenCapture, StripeCallback
+from selkies_b200 import _native as N
+from selkies_b200.session import Session
 from tests import synth
 from tests.test_h264_oracle import split_nals
 
@@ -167,3 +169,36 @@ def test_two_concurrent_sessions_are_independent():
     for t in ts:
         t.join(timeout=120)
     assert out[0] == solo[0] and out[1] == solo[1]
+
+
+def test_ring_release_returns_a_slot_without_encoding():
+    """b2v_ring_release: the producer acquired a slot and then had no frame; the next acquire hands out the same slot and the
+    stream continues as if nothing happened (frame ids stay consecutive)."""
+    w, h = 128, 96
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=30, ring_slots=3) as s:
+        s.submit(synth.desktop(w, h, 0))
+        slot, view = s.acquire()
+        s.release_slot(slot)
+        with pytest.raises(Exception):
+            s.release_slot(slot)                      # already free
+        slot2, view2 = s.acquire()
+        assert slot2 == slot
+        view2[...] = synth.desktop(w, h, 1)
+        s.submit_slot(slot2)
+        s.flush()
+        got = s.take_frames()
+    assert [g.frame_id for g in got] == [0, 1] and got[0].is_key and not got[1].is_key
+
+
+def test_finite_source_ends_without_a_stale_frame():
+    from selkies_b200.pixelflux_compat import ArraySource, CaptureSettings, ScreenCapture
+    w, h = 128, 96
+    frames = [synth.desktop(w, h, t) for t in range(5)]
+    cs = CaptureSettings()
+    cs.capture_width, cs.capture_height, cs.target_fps, cs.h264_crf = w, h, 240.0, 30
+    seen = []
+    cap = ScreenCapture(ArraySource(frames, loop=False))
+    cap.start_capture(cs, lambda p, u: seen.append(p.contents.frame_id))
+    cap._thread.join(10)                              # the capture thread stops by itself when the source is exhausted
+    cap.stop_capture()
+    assert seen == [0, 1, 2, 3, 4]
