@@ -10,7 +10,9 @@
  *
  * Threading: every function is safe to call from any host thread; setters may
  * race with b2v_ring_submit() (reference: control calls arrive on thread-pool
- * threads, media_pipeline.py:195,236,244,300,313).  The frame callback fires on
+ * threads, media_pipeline.py:195,236,244,300,313).  b2v_set_resolution() locks
+ * submitters out, drains, and returns B2V_ESTATE while a producer still holds an
+ * acquired ring slot (its memory is about to be reallocated).  The frame callback fires on
  * the session's own output thread (a native, non-Python thread, as pixelflux's
  * does: media_pipeline.py:293 uses run_coroutine_threadsafe for that reason).
  *
@@ -26,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2V_ABI_VERSION 2
+#define B2V_ABI_VERSION 3
 
 enum {
   B2V_OK = 0,
@@ -59,8 +61,9 @@ typedef struct b2v_settings {
   int32_t rc_mode;          /* B2V_RC_CBR | B2V_RC_CQP                                      */
   int32_t bitrate_kbps;     /* CaptureSettings.h264_bitrate_kbps                            */
   int32_t crf;              /* CaptureSettings.h264_crf → constant QP 0..51 in CQP mode; <0 = 26 */
-  int32_t gop;              /* <=0: IDR only on request (settings.py:163 keyframe_distance=-1);
-                               1: intra-only; N: IDR every N frames                         */
+  int32_t gop;              /* in FRAMES.  <=0: IDR only on request (settings.py:163 keyframe_distance=-1);
+                               1: intra-only; N: IDR every N frames.  keyframe_distance itself is in SECONDS:
+                               the host side passes round(seconds * fps) (pixelflux_compat.py)             */
   int32_t slice_rows;       /* macroblock rows per slice (>=1); 0 = library default (1)      */
   int32_t header_mode;      /* B2V_HDR_*                                                    */
   int32_t ring_slots;       /* pinned BGRA ingest ring depth (2..16); 0 = default 4          */
@@ -113,6 +116,15 @@ typedef struct b2v_stats {
   int64_t n_csc, n_intra, n_inter, n_cavlc, n_slice, n_pack;
   double  ms_csc_device;   /* same launches, timed by the kernel itself (%globaltimer: first block start .. last block end) */
   int64_t n_csc_device;
+  /* host-side stopwatches (CLOCK_MONOTONIC ns, always on): where a session's wall time goes when it is not the GPU's */
+  int64_t ns_wait_event;     /* output thread: waiting for the GPU to finish the next picture (polling, no interrupt)      */
+  int64_t ns_wait_event_max; /*   longest single such wait                                                               */
+  int64_t n_event_sleeps;    /*   waits that outlasted the 30 us busy phase and slept                                    */
+  int64_t ns_wait_job;       /* output thread: idle, no picture in flight                                                */
+  int64_t ns_callback;       /* output thread: inside the frame callback (Python holds the GIL there)                    */
+  int64_t ns_wait_out_slot;  /* submitter: blocked on back-pressure (every output slot in flight)                        */
+  int64_t ns_wait_ring;      /* producer: blocked in b2v_ring_acquire (every ingest slot in flight)                      */
+  int64_t ns_submit;         /* submitter: inside the CUDA enqueue calls of a picture (launches, copies, event records)  */
 } b2v_stats;
 
 /* ---- lifecycle: replaces ScreenCapture() / start_capture / stop_capture
@@ -141,6 +153,8 @@ int   b2v_flush(void* h);                                /* wait until every sub
 int  b2v_set_framerate(void* h, double fps);
 int  b2v_set_bitrate_kbps(void* h, int32_t kbps);
 int  b2v_set_qp(void* h, int32_t qp);                    /* CQP mode (restart-free set_crf) */
+int  b2v_set_gop(void* h, int32_t frames);               /* b2v_settings.gop, live (the Python side converts keyframe_distance
+                                                            SECONDS, settings.py:163, with the current fps) */
 int  b2v_set_resolution(void* h, int32_t src_w, int32_t src_h, int32_t dst_w, int32_t dst_h);
 int  b2v_request_idr(void* h);
 

@@ -48,6 +48,9 @@ class B2VStats(C.Structure):
         ("n_csc", C.c_int64), ("n_intra", C.c_int64), ("n_inter", C.c_int64),
         ("n_cavlc", C.c_int64), ("n_slice", C.c_int64), ("n_pack", C.c_int64),
         ("ms_csc_device", C.c_double), ("n_csc_device", C.c_int64),
+        ("ns_wait_event", C.c_int64), ("ns_wait_event_max", C.c_int64), ("n_event_sleeps", C.c_int64),
+        ("ns_wait_job", C.c_int64), ("ns_callback", C.c_int64), ("ns_wait_out_slot", C.c_int64),
+        ("ns_wait_ring", C.c_int64), ("ns_submit", C.c_int64),
     ]
 
     def as_dict(self):
@@ -71,6 +74,7 @@ SYMBOLS = [
     ("b2v_set_framerate", C.c_int, [C.c_void_p, C.c_double]),
     ("b2v_set_bitrate_kbps", C.c_int, [C.c_void_p, C.c_int32]),
     ("b2v_set_qp", C.c_int, [C.c_void_p, C.c_int32]),
+    ("b2v_set_gop", C.c_int, [C.c_void_p, C.c_int32]),
     ("b2v_set_resolution", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("b2v_request_idr", C.c_int, [C.c_void_p]),
     ("b2v_get_stats", C.c_int, [C.c_void_p, C.POINTER(B2VStats)]),
@@ -113,7 +117,7 @@ def lib():
                 fn = getattr(l, name)          # AttributeError here = header/library mismatch
                 fn.restype = res
                 fn.argtypes = args
-            if l.b2v_abi_version() != 2:
+            if l.b2v_abi_version() != 3:
                 raise ImportError("libb2video ABI version mismatch")
             _lib = l
     return _lib

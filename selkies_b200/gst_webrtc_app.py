@@ -26,7 +26,7 @@ class GSTWebRTCAppError(Exception):
 
 class GSTWebRTCApp:
     def __init__(self, encoder: str = "x264enc", framerate: int = 60, video_bitrate: int = 8000, width: int = 1920,
-                 height: int = 1080, gpu_id: int = 0, keyframe_distance: int = -1, cbr: bool = True, crf: int = 25,
+                 height: int = 1080, gpu_id: int = 0, keyframe_distance: float = -1, cbr: bool = True, crf: int = 25,
                  frame_source: Optional[FrameSource] = None):
         self.encoder = encoder
         self.framerate = framerate

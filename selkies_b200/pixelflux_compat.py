@@ -66,7 +66,7 @@ class CaptureSettings:
         self.watermark_location_enum = 0
         # additions of this implementation (ignored by the reference, which never sets them)
         self.gpu_id = 0                          # settings.py:162 exists but is never forwarded
-        self.keyframe_distance = -1              # settings.py:163
+        self.keyframe_distance = -1              # settings.py:163: SECONDS between key frames; <= 0 = only on request
         self.slice_rows = 0
         self.h264_stripe_rows = 0                # striped mode (h264_fullframe False): macroblock rows per stripe; 0 = about 8 stripes
         self.output_width = 0                    # != capture size => fused bilinear scale
@@ -181,6 +181,8 @@ class ScreenCapture:
         self._thread = None
         self._stop = threading.Event()
         self._lock = threading.RLock()           # control calls arrive on arbitrary executor threads
+        self._resize_lock = threading.Lock()     # capture loop (acquire..submit) vs update_resolution; never held with _lock by the loop
+        self._kf_seconds = -1.0
         self._fps = 60.0
         self._cursor_cb = None
         self.frames_emitted = 0
@@ -208,7 +210,8 @@ class ScreenCapture:
             s.rc_mode = N.B2V_RC_CBR if bool(settings.h264_cbr_mode) else N.B2V_RC_CQP
             s.bitrate_kbps = int(settings.h264_bitrate_kbps)
             s.crf = int(settings.h264_crf)
-            s.gop = int(getattr(settings, "keyframe_distance", -1) or -1)
+            self._kf_seconds = float(getattr(settings, "keyframe_distance", -1) or -1)
+            s.gop = self._gop_frames(self._kf_seconds, s.fps)
             s.slice_rows = int(getattr(settings, "slice_rows", 0) or 0)
             s.header_mode = N.B2V_HDR_PIXELFLUX       # callers strip / keep the 10-byte header themselves
             s.ring_slots = 4
@@ -253,6 +256,11 @@ class ScreenCapture:
                 self._h = None
             self._thread = None
 
+    @staticmethod
+    def _gop_frames(seconds: float, fps: float) -> int:
+        """keyframe_distance is in SECONDS (settings.py:163); b2v_settings.gop is in frames."""
+        return -1 if seconds <= 0 else max(1, int(round(seconds * fps)))
+
     # -- live control ----------------------------------------------------------------------------------
     def update_framerate(self, fps: float) -> None:
         with self._lock:
@@ -260,6 +268,8 @@ class ScreenCapture:
                 return
             N.check(self._lib.b2v_set_framerate(self._h, float(fps)))
             self._fps = float(fps)
+            if self._kf_seconds > 0:               # the key-frame interval is a time: keep it across the rate change
+                N.check(self._lib.b2v_set_gop(self._h, self._gop_frames(self._kf_seconds, self._fps)))
 
     def update_video_bitrate(self, kbps: int) -> None:
         with self._lock:
@@ -275,14 +285,15 @@ class ScreenCapture:
 
     def update_resolution(self, width: int, height: int) -> None:
         """Follow a display resize (what auto_adjust_screen_capture_size does in the reference)."""
-        with self._lock:
-            if self._h is None:
-                return
-            width -= width & 1
-            height -= height & 1
-            N.check(self._lib.b2v_set_resolution(self._h, width, height, 0, 0))
-            self._w, self._h_px = width, height
-            self._source.configure(width, height)
+        with self._resize_lock:                  # the capture loop holds no ring slot while we are in here
+            with self._lock:
+                if self._h is None:
+                    return
+                width -= width & 1
+                height -= height & 1
+                N.check(self._lib.b2v_set_resolution(self._h, width, height, 0, 0))
+                self._w, self._h_px = width, height
+                self._source.configure(width, height)
 
     def set_cursor_callback(self, fn) -> None:       # selkies.py:3166-3167 (guarded by hasattr)
         self._cursor_cb = fn
@@ -292,20 +303,24 @@ class ScreenCapture:
         index = 0
         next_t = time.perf_counter()
         while not self._stop.is_set():
+            # The control lock is held only for the snapshot: acquire (blocks while the ring is full), fill (tens of ms at 4K) and
+            # submit run outside it, so request_idr_frame / update_* never queue behind a frame and a callback that calls them
+            # while the ring is full cannot deadlock.  The handle stays valid: stop_capture joins this thread before destroying it.
             with self._lock:
-                if self._h is None:
-                    break
+                handle, fps = self._h, self._fps
+            if handle is None:
+                break
+            with self._resize_lock:
+                w, h = self._w, self._h_px
                 slot = C.c_int32(-1)
-                p = self._lib.b2v_ring_acquire(self._h, C.byref(slot))
+                p = self._lib.b2v_ring_acquire(handle, C.byref(slot))
                 if not p:
                     break
-                w, h = self._w, self._h_px
                 view = np.frombuffer((C.c_ubyte * (w * h * 4)).from_address(p), np.uint8).reshape(h, w, 4)
                 if not self._source.fill(view, index):
-                    self._lib.b2v_ring_release(self._h, slot.value)      # end of the source: nothing to encode
+                    self._lib.b2v_ring_release(handle, slot.value)      # end of the source: nothing to encode
                     break
-                N.check(self._lib.b2v_ring_submit(self._h, slot.value, w * 4, time.monotonic_ns()))
-                fps = self._fps
+                N.check(self._lib.b2v_ring_submit(handle, slot.value, w * 4, time.monotonic_ns()))
             index += 1
             next_t += 1.0 / max(1e-3, fps)
             delay = next_t - time.perf_counter()

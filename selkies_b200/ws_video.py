@@ -34,22 +34,38 @@ def frames_behind(sent_id: int, acked_id: int) -> int:
     return (sent_id - acked_id) % ID_MODULUS
 
 
-def gate_is_open(sent_id: int, acked_id: int, fps: float, rtt_ms: float, silent_for_s: float) -> bool:
-    """True = keep sending.  `acked_id` < 0: nothing acknowledged yet."""
-    if acked_id < 0 or sent_id == 0:
-        return True
-    if abs(sent_id - acked_id) > (ID_MODULUS - 1) // 2:          # not a lag, a reset on one side: do not act on it
-        return True
+def gate_decision(sent_id: int, acked_id: int, fps: float, rtt_ms: float, silent_for_s: float):
+    """One pass of selkies.py:1218-1260.  Returns (open, reset_stall_timer); open is True (send), False (hold) or None (leave the
+    gate as it is: the server has not sent frame id 0 -> N yet, selkies.py:1239)."""
+    if acked_id < 0:                                             # nothing acknowledged yet (:1221-1226)
+        return True, True
+    if abs(sent_id - acked_id) > (ID_MODULUS - 1) // 2:          # not a lag, a reset on one side (:1234-1237)
+        return True, True
+    if sent_id == 0:
+        return None, False
     if silent_for_s > STALL_AFTER_S:
-        return False
+        return False, False
     fps = fps if fps > 0 else 60.0
     credit = rtt_ms / 1000.0 * fps if rtt_ms > RTT_CREDIT_ABOVE_MS else 0.0
-    return frames_behind(sent_id, acked_id) - credit <= ALLOWED_LAG_MS / 1000.0 * fps
+    return frames_behind(sent_id, acked_id) - credit <= ALLOWED_LAG_MS / 1000.0 * fps, False
+
+
+def gate_is_open(sent_id: int, acked_id: int, fps: float, rtt_ms: float, silent_for_s: float, was_open: bool = True) -> bool:
+    """True = keep sending.  `acked_id` < 0: nothing acknowledged yet."""
+    o, _ = gate_decision(sent_id, acked_id, fps, rtt_ms, silent_for_s)
+    return was_open if o is None else o
 
 
 class WsVideoChannel:
     def __init__(self, send: Callable[[bytes], Awaitable[None]], loop: Optional[asyncio.AbstractEventLoop] = None,
                  queue_depth: int = 120, fps: float = 60.0, jpeg: bool = False, clock=time.monotonic):
+        # `on_stripe` runs on the encoder's native thread, which has no event loop of its own: the loop is fixed HERE (the
+        # reference captures it the same way, selkies.py:3132 uses the server's loop), never looked up from the callback.
+        if loop is None:
+            try:
+                loop = asyncio.get_running_loop()
+            except RuntimeError:
+                raise RuntimeError("WsVideoChannel needs an event loop: construct it inside the loop or pass loop=") from None
         self._send, self._loop, self._clock = send, loop, clock
         self.queue: asyncio.Queue = asyncio.Queue(maxsize=queue_depth)
         self.fps, self.jpeg = fps, jpeg
@@ -71,8 +87,7 @@ class WsVideoChannel:
         chunk = bytes(res.data[:res.size])
         if self.jpeg:
             chunk = b"\x03\x00" + chunk           # JPEG stripes carry a 2-byte type prefix (selkies.py:3118)
-        loop = self._loop or asyncio.get_event_loop()
-        loop.call_soon_threadsafe(self._offer, chunk, int(res.frame_id))
+        self._loop.call_soon_threadsafe(self._offer, chunk, int(res.frame_id))
 
     def _offer(self, chunk: bytes, frame_id: int) -> None:
         try:
@@ -117,10 +132,12 @@ class WsVideoChannel:
         return sum(self._rtts) / len(self._rtts) if self._rtts else 0.0
 
     def evaluate_gate(self, client_fps: float = 0.0) -> bool:
-        if self.acked_id < 0:
-            self.last_ack_at = self._clock()      # the stall timer only runs once the client has acknowledged something
-        self.open = gate_is_open(self.last_sent_id, self.acked_id, client_fps or self.fps, self.rtt_ms,
+        o, reset = gate_decision(self.last_sent_id, self.acked_id, client_fps or self.fps, self.rtt_ms,
                                  self._clock() - self.last_ack_at)
+        if reset:
+            self.last_ack_at = self._clock()      # no ACK yet / implausible id gap: the stall timer restarts (selkies.py:1225, 1236)
+        if o is not None:
+            self.open = o
         return self.open
 
     async def run_gate(self, client_fps: Callable[[], float] = lambda: 0.0) -> None:

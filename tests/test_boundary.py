@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/b2video.h but not exported"
     bound = {n for n, _, _ in _native.SYMBOLS}
     assert set(declared) == bound, set(declared) ^ bound
-    assert _native.lib().b2v_abi_version() == 2          # no compute call: safe without a GPU
+    assert _native.lib().b2v_abi_version() == 3          # no compute call: safe without a GPU
 
 
 def test_struct_layouts_match_header():
@@ -34,6 +34,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(N.B2VSettings) == 4 * 4 + 8 + 9 * 4 + 4 * 4 + 4    # padded to 8
     assert ctypes.sizeof(N.B2VFrame) == 8 + 4 * 4 + 8 + 8 + 2 * 4 and N.B2VFrame.y_start.offset == 40
     assert N.B2VSettings.fps.offset == 16 and N.B2VSettings.device.offset == 24
+    assert ctypes.sizeof(N.B2VStats) == 7 * 8 + 7 * 8 + 6 * 8 + 2 * 8 + 8 * 8 and N.B2VStats.ns_wait_event.offset == 22 * 8
 
 
 def test_product_never_imports_the_oracle():
@@ -203,3 +204,13 @@ def test_c_abi_argument_errors_without_a_gpu():
     assert lib.b2v_rtp_h264_packetize(None, 0, 1300, None, 0, None, 0, C.byref(n)) == N.B2V_EINVAL
     with pytest.raises(N.B2VError):
         N.check(N.B2V_EINVAL)
+
+
+def test_keyframe_distance_is_seconds():
+    """settings.py:163: keyframe_distance is in seconds; b2v_settings.gop is in frames."""
+    from selkies_b200.pixelflux_compat import ScreenCapture
+    assert ScreenCapture._gop_frames(-1, 60.0) == -1
+    assert ScreenCapture._gop_frames(0, 60.0) == -1
+    assert ScreenCapture._gop_frames(2, 60.0) == 120
+    assert ScreenCapture._gop_frames(1, 30.0) == 30
+    assert ScreenCapture._gop_frames(0.001, 30.0) == 1

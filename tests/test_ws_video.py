@@ -75,3 +75,30 @@ def test_jpeg_prefix():
         task.cancel()
         assert got == [b"\x03\x00JFIF"]
     asyncio.run(run())
+
+
+def test_gate_keeps_state_before_first_frame_and_resets_stall_timer():
+    """selkies.py:1239 (`if server_id == 0: continue`) leaves the gate as it is; :1225 / :1236 restart the stall timer."""
+    from selkies_b200.ws_video import gate_decision, gate_is_open
+    assert gate_decision(0, 5, 60.0, 0.0, 0.0) == (None, False)
+    assert gate_is_open(0, 5, 60.0, 0.0, 0.0, was_open=False) is False      # a closed gate stays closed
+    assert gate_is_open(0, 5, 60.0, 0.0, 0.0, was_open=True) is True
+    assert gate_decision(100, -1, 60.0, 0.0, 99.0) == (True, True)            # no ACK yet: open + timer restart
+    assert gate_decision(40000, 10, 60.0, 0.0, 99.0) == (True, True)          # implausible gap: open + timer restart
+    assert gate_decision(100, 90, 60.0, 0.0, 5.0) == (False, False)           # silent client
+
+
+def test_channel_requires_an_event_loop_at_construction():
+    """The callback thread has no loop of its own: a channel built without one must fail at construction, not lose stripes."""
+    import pytest
+    from selkies_b200.ws_video import WsVideoChannel
+
+    async def send(_):
+        pass
+    with pytest.raises(RuntimeError):
+        WsVideoChannel(send)                   # no running loop, none given
+
+    async def inside():
+        return WsVideoChannel(send)            # picks up the running loop
+    ch = asyncio.run(inside())
+    assert ch._loop is not None
