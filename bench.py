@@ -47,7 +47,7 @@ def synth_frames(n, w=W, h=H):
 
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  One nvidia-smi process
-    (rank 0 only, all GPUs of the job, 50 ms period) is started before the warm-up so that it is already streaming when the
+    (rank 0 only, all GPUs of the job, 100 ms period) is started before the warm-up so that it is already streaming when the
     timed region begins; `mark()` / `stop()` delimit the rows that fall inside it."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -74,19 +74,19 @@ class ClockSampler:
     def stop(self):
         t_end = time.monotonic()
         if self.proc:
-            time.sleep(0.06)                 # let the sample that was being taken at t_end arrive
+            time.sleep(0.11)                 # let the sample that was being taken at t_end arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
         mine = [(t, r) for t, r in self.rows if len(r) >= 8 and r[0].isdigit() and int(r[0]) < self.n_gpus]
-        inside = [r for t, r in mine if self.t_mark is not None and self.t_mark <= t <= t_end + 0.06]
+        inside = [r for t, r in mine if self.t_mark is not None and self.t_mark <= t <= t_end + 0.11]
         window = "timed region"
         if not inside and mine:              # region shorter than one sampling period: the samples bracketing it
             t0 = self.t_mark if self.t_mark is not None else t_end
             near = sorted(mine, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t_end)))[: 2 * self.n_gpus]
-            inside, window = [r for _, r in near], "nearest samples (region shorter than the 50 ms period)"
+            inside, window = [r for _, r in near], "nearest samples (region shorter than the 100 ms period)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in inside:
@@ -168,18 +168,33 @@ def usable_threads() -> int:
     return max(1, min(n, int(q + 0.999))) if q else n
 
 
-def cpu_sample(frames, n_p: int, threads: int | None = None):
-    """Oracle CSC + encode of 1 IDR + n_p P pictures on the host cores; returns (P frames/s, seconds, threads)."""
+def cpu_sample(frames, n_p: int, threads: int | None = None, keep=None):
+    """Oracle CSC + encode of 1 IDR + n_p P pictures on the host cores; returns (P frames/s, seconds, threads).  `keep`: a list
+    that receives the access units (the checker's output, compared with the GPU's by parity_leg)."""
     import oracle
     used = oracle.set_threads(threads or usable_threads())
     enc = oracle.RefEncoder(W, H)
     target = int(BITRATE_KBPS * 1000 / FPS_NOMINAL)
-    enc.encode_bgra(frames[0], True, rc_mode=0, target_bits=target)
+    au = enc.encode_bgra(frames[0], True, rc_mode=0, target_bits=target)
+    if keep is not None:
+        keep.append(au)
     t0 = time.perf_counter()
     for i in range(n_p):
-        enc.encode_bgra(frames[(i + 1) % len(frames)], False, rc_mode=0, target_bits=target)
+        au = enc.encode_bgra(frames[(i + 1) % len(frames)], False, rc_mode=0, target_bits=target)
+        if keep is not None:
+            keep.append(au)
     dt = time.perf_counter() - t0
     return n_p / dt, dt, used
+
+
+def x264_anchor(cores: int):
+    """The only published number for the reference's own CPU encoder: docs/design.md:33 — 1080p60 costs about 1.5 cores of
+    x264enc (ultrafast/zerolatency) + videoconvert.  Scaled by pixel count (4K = 4 x 1080p) that is ~6 cores for 4K60, i.e.
+    ~10 pictures/s per core; on `cores` host cores ~10*cores pictures/s.  An ESTIMATE from a published anchor on other
+    hardware, not a measurement: x264 / GStreamer are absent from this image."""
+    per_core = 60.0 / (1.5 * 4.0)
+    return {"frames_per_s_estimate": per_core * cores, "cores": cores, "per_core": per_core,
+            "source": "reference docs/design.md:33 (1080p60 ~ 150 % CPU), scaled x4 pixels; estimate, not measured here"}
 
 
 def run_reference(args, rank, world):
@@ -235,6 +250,109 @@ def rtp_leg(aus):
                 "python_reference_port_us_per_au": t_py * 1e6, "identical_payloads": same}
     except Exception as e:
         return {"error": repr(e)}
+
+
+HOST_KEYS = ("ns_wait_event", "ns_wait_job", "ns_callback", "ns_wait_out_slot", "ns_wait_ring", "ns_submit")
+
+
+def host_breakdown(st1, st0, n_frames):
+    """Where this session's HOST threads spent the leg, in microseconds per picture (b2v_stats stopwatches): the output thread
+    waiting for the GPU / idle / inside the callback, the submitter blocked on back-pressure or inside CUDA enqueue calls."""
+    d = {k[3:] + "_us": (st1[k] - (st0[k] if st0 else 0)) / 1e3 / max(1, n_frames) for k in HOST_KEYS}
+    d["wait_event_max_us"] = st1["ns_wait_event_max"] / 1e3
+    d["event_sleeps_per_frame"] = (st1["n_event_sleeps"] - (st0["n_event_sleeps"] if st0 else 0)) / max(1, n_frames)
+    return d
+
+
+def resident_leg(frames, n_pics, device, *, w=W, h=H, warm=32, collect_sizes=False, **kw):
+    """Side measurement: `n_pics` pictures of `frames` (cycled, resident in HBM) through a fresh session, device-timed."""
+    from selkies_b200.session import Session
+    nb = [0, 0]
+
+    def on_frame(fptr):
+        nb[0] += fptr.contents.size; nb[1] += 1
+    with Session(w, h, device=device, collect=False, on_frame=on_frame, **kw) as ss:
+        for i, f in enumerate(frames):
+            ss.resident_upload(i, f)
+        for k in range(warm):
+            ss.submit_resident(k % len(frames))
+        ss.flush(); nb[0] = nb[1] = 0
+        ss.timer_start()
+        for k in range(n_pics):
+            ss.submit_resident((warm + k) % len(frames))
+        ms = ss.timer_stop()
+    return {"value": n_pics / (ms / 1000.0), "unit": "frames/s", "ms_per_picture": ms / n_pics, "pictures": n_pics,
+            "bytes_per_picture": nb[0] / max(1, n_pics), "callbacks_per_picture": nb[1] / max(1, n_pics)}
+
+
+def parity_leg(frames, ref_aus, device):
+    """The first len(ref_aus) access units of the bench stream (fresh session, same settings and entry point as the timed leg)
+    compared byte for byte with the checker's (oracle) output for the same pictures."""
+    from selkies_b200 import _native as N
+    from selkies_b200.session import Session
+    with Session(W, H, fps=FPS_NOMINAL, device=device, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS, ring_slots=N_DISTINCT,
+                 flags=N.B2V_FLAG_TIMING_CSC) as sp:
+        for i, f in enumerate(frames):
+            sp.resident_upload(i, f)
+        for i in range(len(ref_aus)):
+            sp.submit_resident(i % len(frames))
+        sp.flush()
+        got = sp.take_frames()
+    bad = [i for i, (g, r) in enumerate(zip(got, ref_aus)) if g.data != r]
+    return {"parity_checked": len(ref_aus), "parity_ok": not bad and len(got) == len(ref_aus), "first_mismatch": bad[0] if bad else None,
+            "what": "access-unit bytes, GPU vs oracle, 1 IDR + P pictures of the timed workload (incl. the scroll restart at picture 16)"}
+
+
+def python_surface_leg(frames, device, seconds=2.0):
+    """SURVEY §7 / VERDICT r1 Missing #8: 4K throughput through the reference-facing PYTHON surface — pixelflux_compat.ScreenCapture
+    fed by an ArraySource (a numpy copy of every 33 MB frame into the pinned slot, the job of the reference's XShm grab), the
+    callback doing what media_pipeline.py:286 does: bytes(result.data[10:result.size])."""
+    from selkies_b200.pixelflux_compat import ArraySource, CaptureSettings, ScreenCapture
+    n, nbytes = [0], [0]
+
+    def cb(result_ptr, _user):
+        if not result_ptr:
+            return
+        r = result_ptr.contents
+        au = bytes(r.data[10:r.size])
+        n[0] += 1; nbytes[0] += len(au)
+    cs = CaptureSettings()
+    cs.capture_width, cs.capture_height, cs.target_fps = W, H, 1000.0       # free-running: the source never has to wait
+    cs.h264_cbr_mode, cs.h264_bitrate_kbps, cs.gpu_id = True, BITRATE_KBPS, device
+    cap = ScreenCapture(ArraySource(frames, loop=True))
+    cap.start_capture(cs, cb)
+    time.sleep(0.5)
+    n0, t0 = n[0], time.perf_counter()
+    time.sleep(seconds)
+    n1, t1 = n[0], time.perf_counter()
+    cap.stop_capture()
+    return {"value": (n1 - n0) / (t1 - t0), "unit": "frames/s", "seconds": t1 - t0,
+            "note": "ScreenCapture + ArraySource(4K) -> callback bytes(result.data[10:size]); includes the producer's 33 MB numpy copy "
+                    "into the pinned slot per frame (single Python thread), H2D, encode, D2H"}
+
+
+def live_csc_traffic(timeout_s=240):
+    """dram__bytes_read/write of one 4K CSC launch, measured NOW on this box with this build: a short ncu run (separate process,
+    CSC-only session, outside every timed region).  None when ncu cannot run here."""
+    import csv, io, shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    try:
+        out = subprocess.run([ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:csc_bgra_nv12",
+                              "-s", "4", "-c", "4", "--csv", sys.executable, os.path.join(ROOT, "tools", "csc_once.py")],
+                             capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        rows = [r for r in csv.reader(io.StringIO(out.stdout)) if len(r) > 10]
+        hdr = rows[0]
+        im, iv, iu = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = [float(r[iv].replace(",", "")) * scale.get(r[iu], 1) for r in rows[1:] if r[im] == "dram__bytes_read.sum"]
+        wr = [float(r[iv].replace(",", "")) * scale.get(r[iu], 1) for r in rows[1:] if r[im] == "dram__bytes_write.sum"]
+        if not rd or not wr:
+            return None
+        return {"read": sum(rd) / len(rd), "write": sum(wr) / len(wr), "launches": len(rd), "source": "live ncu run inside bench.py (tools/csc_once.py)"}
+    except Exception:
+        return None
 
 
 def workload_config(frames_per_step):
@@ -311,6 +429,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return [float(v) for v in t.tolist()]
 
+    def gather_dict(d: dict):
+        """{key: [value on rank 0, rank 1, ...]} for a flat dict of floats"""
+        keys = sorted(d)
+        if world == 1:
+            return {k: [d[k]] for k in keys}
+        t = torch.zeros(world, len(keys), dtype=torch.float64, device="cuda")
+        t[rank] = torch.tensor([float(d[k]) for k in keys], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return {k: [float(v) for v in t[:, i].tolist()] for i, k in enumerate(keys)}
+
     def sum_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -364,7 +492,9 @@ def main():
     n_frames = args.steps * FRAMES_PER_STEP
     t_ms = max_over_ranks(max(dev_ms, 0.0))
     per_rank_ms = gather_over_ranks(max(dev_ms, 0.0))
+    per_rank_wall_ms = gather_over_ranks(wall_ms)
     value = sum_over_ranks(float(n_frames)) / (t_ms / 1000.0)
+    host_resident = gather_dict(host_breakdown(st, None, n_frames))       # reset_stats ran right before the leg
 
     # ---------------- leg 2: end to end from pinned host buffers -----------------------------------------
     # pre-fill the pinned ring once (the producer — XShm grab in the reference — writes into these slots);
@@ -397,6 +527,8 @@ def main():
     st1 = sess.stats()
     e2e_ms = max_over_ranks(max(e2e_wall_ms, e2e_dev_ms))
     e2e_value = sum_over_ranks(float(n_frames)) / (e2e_ms / 1000.0)
+    per_rank_e2e_ms = gather_over_ranks(max(e2e_wall_ms, e2e_dev_ms))
+    host_e2e = gather_dict(host_breakdown(st1, st0, n_frames))
     h2d_step = (st1["h2d_bytes"] - st0["h2d_bytes"]) / args.steps
     d2h_step = (st1["d2h_bytes"] - st0["d2h_bytes"]) / args.steps
 
@@ -406,6 +538,10 @@ def main():
     achieved = alg / (csc_ms * 1e-3) / 1e9 if csc_ms > 0 else 0.0
     burst_ms = sess.bench_csc_burst(N_DISTINCT, 200)
     traffic = csc_dram_traffic()
+    if rank == 0 and world == 1:
+        live = live_csc_traffic()
+        if live:
+            traffic = (live["read"] + live["write"], live["read"], live["write"], live["source"])
     roofline = {"bound": "hbm", "kernel": "csc_bgra_nv12_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic[0], "traffic_read": traffic[1], "traffic_write": traffic[2], "traffic_source": traffic[3],
                 "algorithmic_bytes_per_launch": alg, "us_per_launch": csc_ms * 1e3,
@@ -477,43 +613,60 @@ def main():
         except Exception as e:
             roofline["c4_8k_stress"] = {"error": repr(e)}
 
-    # ---------------- striped mode: same frames, 8 independent stripes per picture ------------------
-    striped = None
+    # ---------------- side legs (rank 0): striped mode, IDR / C1, worst-case contents, the Python surface ----------------
+    striped = idr_legs = content_legs = py_surface = None
     if rank == 0:
-        try:
-            n_str, n_cb = [0], [0]
+        cbr = dict(fps=FPS_NOMINAL, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS, ring_slots=4)
+        try:      # same frames, 8 independent stripes per picture
             rows = -(-(H // 16) // 8)
-            with Session(W, H, fps=FPS_NOMINAL, device=local_rank, rc_mode=N.B2V_RC_CBR, bitrate_kbps=BITRATE_KBPS, ring_slots=4,
-                         stripe_rows=rows, header_mode=N.B2V_HDR_PIXELFLUX, collect=False) as ss:
-                def on_stripe(fptr):
-                    n_cb[0] += 1; n_str[0] += fptr.contents.size
-                ss._on_frame = on_stripe
-                for i, f in enumerate(frames):
-                    ss.resident_upload(i, f)
-                for kk in range(48):
-                    ss.submit_resident(kk % N_DISTINCT)
-                ss.flush(); n_cb[0] = n_str[0] = 0
-                ss.timer_start()
-                for kk in range(N_SIDE):
-                    ss.submit_resident(kk % N_DISTINCT)
-                ms = ss.timer_stop()
-            striped = {"stripe_rows": rows, "stripes_per_picture": -(-(H // 16) // rows), "value": N_SIDE / (ms / 1000.0), "unit": "frames/s",
-                       "stripes_delivered_per_picture": n_cb[0] / N_SIDE, "bytes_per_picture": n_str[0] / N_SIDE,
-                       "note": "inputs resident in HBM, 256 pictures; stripes whose macroblocks were all skipped are not delivered"}
+            striped = resident_leg(frames, N_SIDE, local_rank, warm=48, stripe_rows=rows, header_mode=N.B2V_HDR_PIXELFLUX, **cbr)
+            striped.update({"stripe_rows": rows, "stripes_per_picture": -(-(H // 16) // rows),
+                            "stripes_delivered_per_picture": striped.pop("callbacks_per_picture"),
+                            "note": "inputs resident in HBM, 256 pictures; stripes whose macroblocks were all skipped are not delivered"})
         except Exception as e:
             striped = {"error": repr(e)}
+        try:      # the IDR path (PLI -> key frame, rtc.py:601-603) and BASELINE configs[1] (1080p60, I-only)
+            from tests import synth
+            i4k = resident_leg(frames, 48, local_rank, warm=8, gop=1, **cbr)
+            i4q = resident_leg(frames, 48, local_rank, warm=8, gop=1, fps=FPS_NOMINAL, rc_mode=N.B2V_RC_CQP, crf=30, ring_slots=4)
+            f1080 = [synth.desktop(1920, 1080, t) for t in range(N_DISTINCT)]
+            c1 = resident_leg(f1080, 128, local_rank, w=1920, h=1080, warm=16, gop=1, fps=60.0, rc_mode=N.B2V_RC_CQP, crf=25, ring_slots=4)
+            idr_legs = {"idr_4k_ms": i4k["ms_per_picture"], "i_only_4k_fps": i4k["value"], "idr_4k_bytes": i4k["bytes_per_picture"],
+                        "idr_4k_qp30_ms": i4q["ms_per_picture"], "idr_4k_qp30_bytes": i4q["bytes_per_picture"],
+                        "c1_1080p_i_only_fps": c1["value"], "c1_1080p_idr_ms": c1["ms_per_picture"], "c1_bytes_per_picture": c1["bytes_per_picture"],
+                        "note": "gop=1 (every picture an IDR with in-band SPS/PPS), inputs resident; 4K: CBR 20 Mbit/s; C1 = BASELINE configs[1] "
+                                "1920x1080 synthetic desktop, constant QP 25 (the reference's default h264_crf, settings.py:48), target 60 fps"}
+        except Exception as e:
+            idr_legs = {"error": repr(e)}
+        try:      # worst-case contents: S2 uniform noise (nothing predictable, every MB searched + refined), S4 gradient pan
+            from tests import synth
+            s2 = resident_leg([synth.noise(W, H, 100 + t) for t in range(4)], 96, local_rank, warm=16, **cbr)
+            s4 = resident_leg([synth.gradient(W, H, t) for t in range(N_DISTINCT)], 128, local_rank, warm=32, **cbr)
+            content_legs = {"s2_noise_fps": s2["value"], "s2_bytes_per_picture": s2["bytes_per_picture"],
+                            "s4_gradient_pan_fps": s4["value"], "s4_bytes_per_picture": s4["bytes_per_picture"],
+                            "note": "same session settings as the headline leg (4K, CBR 20 Mbit/s), inputs resident; S2 = fresh uniform noise every picture "
+                                    "(worst case: every macroblock runs the exhaustive search + refinement), S4 = smooth gradient panning 2 px/picture"}
+        except Exception as e:
+            content_legs = {"error": repr(e)}
+        try:
+            py_surface = python_surface_leg(frames, local_rank)
+        except Exception as e:
+            py_surface = {"error": repr(e)}
 
     # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) ------------------------------------------
-    cpu = None
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             one_fps, one_dt, _ = cpu_sample(frames, 2, threads=1)
-            all_fps, all_dt, cores = cpu_sample(frames, 24, threads=None)
+            ref_aus = []
+            all_fps, all_dt, cores = cpu_sample(frames, 24, threads=None, keep=ref_aus)
+            parity = parity_leg(frames, ref_aus, local_rank)
             cpu = {"value": all_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "1 IDR + 24 P pictures 3840x2160 (oracle CSC + encode, OpenMP over macroblock rows), IDR untimed; "
                              f"1 thread: {one_fps:.3f} frames/s over 2 P pictures",
                    "single_thread_value": one_fps,
-                   "cgroup_cpu_quota": cpu_quota(), "note": "CPU restatement of this repo's encoder, not x264/videoconvert (absent from the image)"}
+                   "cgroup_cpu_quota": cpu_quota(), "note": "CPU restatement of this repo's encoder, not x264/videoconvert (absent from the image)",
+                   "x264_anchor": x264_anchor(cores)}
         except Exception as e:  # the checker failing must not hide the GPU number
             cpu = {"value": None, "error": repr(e)}
 
@@ -523,9 +676,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(FRAMES_PER_STEP),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                    "wall_ms": e2e_wall_ms, "device_ms": e2e_dev_ms, "access_unit_bytes_per_frame": out_bytes[0] / max(1, n_frames)},
+                    "wall_ms": e2e_wall_ms, "device_ms": e2e_dev_ms, "access_unit_bytes_per_frame": out_bytes[0] / max(1, n_frames),
+                    "producer": "excluded: the pinned ring is pre-filled once (screen capture is out of scope, SURVEY.md §8b); the H2D copy of every "
+                                "33 MB picture and the D2H copy of every access unit are inside the timed region; `python_surface` has a leg with a producer"},
             "gpu_launches": int(st["kernel_launches"]), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "kernels_us": kern, "per_rank_ms_resident": per_rank_ms, "per_rank_span_us": per_rank_span, "per_rank_inter_us": per_rank_inter, "per_rank_numa": per_rank_numa, "numa_node": numa, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus), "striped_mode": striped,
+            "kernels_us": kern, "per_rank_ms_resident": per_rank_ms, "per_rank_wall_ms_resident": per_rank_wall_ms, "per_rank_ms_e2e": per_rank_e2e_ms,
+            "per_rank_host_us_per_frame": {"resident": host_resident, "e2e": host_e2e,
+                                           "keys": "output thread: wait_event (GPU not done yet), wait_job (idle), callback; submitter: wait_out_slot (back-pressure), wait_ring, submit (CUDA enqueue calls)"},
+            "parity": parity, "idr": idr_legs, "content_legs": content_legs, "python_surface": py_surface, "per_rank_span_us": per_rank_span, "per_rank_inter_us": per_rank_inter, "per_rank_numa": per_rank_numa, "numa_node": numa, "wall_ms_resident": wall_ms, "target_fps": 240, "rtp_payloader": rtp_leg(sample_aus), "striped_mode": striped,
         }
         emit(line)
     if world > 1:
