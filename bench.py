@@ -613,6 +613,27 @@ def main():
         except Exception as e:
             roofline["c4_8k_stress"] = {"error": repr(e)}
 
+    # ---------------- fused scale + CSC legs: 4K -> 1080p and 1080p -> 4K, same event-pair timing as the 1:1 kernel ----
+    if rank == 0:
+        try:
+            from tests import synth
+            sc = {}
+            for (sw, sh, dw, dh) in ((3840, 2160, 1920, 1080), (1920, 1080, 3840, 2160)):
+                with Session(sw, sh, dst_width=dw, dst_height=dh, device=local_rank, flags=N.B2V_FLAG_NO_ENCODE) as sx:
+                    nres = 8 if sw > 2000 else 24
+                    base = synth.desktop(sw, sh, 0)
+                    for i in range(nres):
+                        sx.resident_upload(i, np.roll(base, 8 * i, axis=0))
+                    ms_e, ms_b = sx.bench_csc(nres, 100), sx.bench_csc_burst(nres, 100)
+                algs = 4.0 * sw * sh + 1.5 * dw * dh
+                sc[f"{sw}x{sh}_to_{dw}x{dh}"] = {"us_per_launch": ms_e * 1e3, "burst_us_per_launch": ms_b * 1e3, "algorithmic_bytes_per_launch": algs,
+                                                 "achieved": algs / (ms_e * 1e-3) / 1e9, "frac": algs / (ms_e * 1e-3) / 1e9 / peak,
+                                                 "burst_frac": algs / (ms_b * 1e-3) / 1e9 / peak}
+            sc["note"] = "csc_bgra_nv12_scaled (shared-memory tile, bilinear + BT.709 in one pass); bytes = 4 B x source px + 1.5 B x output px; one CUDA-event pair per launch"
+            roofline["scaled"] = sc
+        except Exception as e:
+            roofline["scaled"] = {"error": repr(e)}
+
     # ---------------- side legs (rank 0): striped mode, IDR / C1, worst-case contents, the Python surface ----------------
     striped = idr_legs = content_legs = py_surface = None
     if rank == 0:

@@ -68,9 +68,10 @@ typedef struct b2v_settings {
   int32_t header_mode;      /* B2V_HDR_*                                                    */
   int32_t ring_slots;       /* pinned BGRA ingest ring depth (2..16); 0 = default 4          */
   int32_t flags;            /* B2V_FLAG_*                                                   */
-  int32_t paintover_trigger_frames; /* CQP mode: after this many consecutive all-skipped pictures code ONE picture at
-                                       paintover_crf (CaptureSettings.paint_over_trigger_frames / use_paint_over_quality,
-                                       selkies.py:3226-3229); 0 = off */
+  int32_t paintover_trigger_frames; /* after this many consecutive all-skipped pictures code paintover_burst_frames pictures
+                                       at paintover_crf (CaptureSettings.paint_over_trigger_frames / use_paint_over_quality,
+                                       selkies.py:3226-3229); in CBR mode the paint-over QP only applies when it is finer
+                                       than the controller's; 0 = off */
   int32_t paintover_crf;            /* CaptureSettings.h264_paintover_crf */
   int32_t stripe_rows;      /* striped mode (CaptureSettings.h264_fullframe = False, selkies.py:3219; encoder
                                "x264enc-striped"): macroblock rows per stripe, a multiple of slice_rows.  Every stripe is
@@ -78,7 +79,8 @@ typedef struct b2v_settings {
                                delivered by its own callback with y_start/height (10-byte header bytes 4..9,
                                selkies-ws-core.js:3183-3196); a stripe whose macroblocks were all skipped is not
                                delivered.  0 or >= picture rows = full frame */
-  int32_t reserved[1];
+  int32_t paintover_burst_frames;   /* CaptureSettings.h264_paintover_burst_frames (selkies.py:3217): how many consecutive
+                                       pictures are coded at paintover_crf once the trigger is reached; <= 0 = 1 */
 } b2v_settings;
 
 enum {

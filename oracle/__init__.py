@@ -107,8 +107,10 @@ class RefEncoder:
         n = self.L.b2v_ref_enc_stripe_table(self.h, t.ctypes.data_as(C.POINTER(C.c_int32)))
         return [tuple(int(v) for v in t[3 * i: 3 * i + 3]) for i in range(n)]
 
-    def set_paintover(self, trigger_frames: int, qp: int) -> None:
+    def set_paintover(self, trigger_frames: int, qp: int, burst_frames: int = 1) -> None:
         self.L.b2v_ref_enc_set_paintover(self.h, trigger_frames, qp)
+        self.L.b2v_ref_enc_set_paintover_burst.argtypes = [C.c_void_p, C.c_int]
+        self.L.b2v_ref_enc_set_paintover_burst(self.h, burst_frames)
 
     def encode_nv12(self, y: np.ndarray, uv: np.ndarray, idr: bool, rc_mode: int = 1, qp: int = 26, target_bits: int = 0) -> bytes:
         assert y.shape == (self.ch, self.cw) and uv.shape == (self.ch // 2, self.cw)

@@ -29,7 +29,9 @@
  *     argmin of (cost << 11 | (dy+16)*32 + (dx+16)); the search is skipped (mv = 0) when SAD(0,0) <= 96*lambda(qp);
  *     then half- and quarter-sample refinement (6-tap interpolation, 8 + 8 candidates) around the full-sample winner
  *   - quantisation: |l| = (|w|*MF + f) >> (15+qp/6), f = 2^(15+qp/6)/3 intra, /6 inter, |l| clamped to 2047
- *   - constant QP inside a picture; picture QP from the frame-level rate controller below
+ *   - constant QP inside a picture; picture QP from the frame-level rate controller below.  The controller's feedback reaches
+ *     the encoder TWO pictures late (picture k is coded with the controller state left by picture k-2): on the GPU the
+ *     entropy coding of picture k-1 — where its size becomes known — overlaps the analysis of picture k
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -99,9 +101,11 @@ typedef struct {
   int cur;
   mb_t* mbs;
   int frame_num, idr_count;
-  /* rate controller */
-  int rc_qp; int64_t rc_fullness;
-  int static_run, paint_trigger, paint_qp;   /* CQP paint-over: one finer picture after `paint_trigger` all-skipped pictures */
+  /* rate controller / paint-over scheduler: fb[k & 1] is the feedback record written after picture k; picture k is coded from
+   * fb[k & 1] as it stood BEFORE that, i.e. the state after picture k-2 (see rc_step) */
+  struct rcfb { int32_t qp, static_run, remaining, paint; int64_t fullness, X; } fb[2];
+  int64_t pic;            /* pictures encoded so far */
+  int paint_trigger, paint_qp, paint_burst;   /* paint-over: `paint_burst` finer pictures after `paint_trigger` all-skipped pictures */
   int last_qp; int64_t last_bits;
   uint8_t sps[64], pps[32]; int sps_len, pps_len;
   /* striped mode (pixelflux h264_fullframe = False): the picture is cut into bands of stripe_rows macroblock rows, each an
@@ -1041,19 +1045,79 @@ static int rc_initial_qp(int64_t target_bits, int mbs) {
   int64_t per_mb = target_bits / (mbs > 0 ? mbs : 1);
   return per_mb >= 400 ? 22 : per_mb >= 200 ? 26 : per_mb >= 100 ? 30 : per_mb >= 50 ? 34 : per_mb >= 25 ? 38 : 42;
 }
-static void rc_update(enc_t* e, int64_t bits, int64_t target, int idr) {
-  if (target < 1) target = 1;
-  int64_t ref = idr ? 4 * target : target;
-  int64_t r = bits * 16 / ref;
-  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 1 ? -4 : r <= 4 ? -2 : r <= 13 ? -1 : 0;   /* r <= 1: (nearly) all-skip picture -> refine quickly */
-  e->rc_fullness += bits - target;
-  if (e->rc_fullness < -4 * target) e->rc_fullness = -4 * target;
-  if (e->rc_fullness > 16 * target) e->rc_fullness = 16 * target;
-  /* bucket over-full (typically after a key frame): raise the QP — unless this picture used under a quarter of its budget
-   * (static scene: the debt is being repaid anyway, a coarser QP would only blur it); then at most one step finer per picture */
-  if (e->rc_fullness > 4 * target) { if (r > 4) { if (dq < 1) dq = 1; } else if (dq < -1) dq = -1; }
-  if (e->rc_fullness < -2 * target && dq > -1) dq = -1;
-  e->rc_qp = clip3(10, 48, e->rc_qp + dq);
+/* Quantiser step in Q6 (64 * 2^(qp/6)): the P-picture model is  bits(qp) = X / QS[qp]. */
+static const int32_t RC_QS[52] = {
+  64, 72, 81, 91, 102, 114, 128, 144, 161, 181, 203, 228, 256, 287, 323, 362, 406, 456, 512, 575, 645, 724, 813, 912, 1024, 1149,
+  1290, 1448, 1625, 1825, 2048, 2299, 2580, 2896, 3251, 3649, 4096, 4598, 5161, 5793, 6502, 7298, 8192, 9195, 10321, 11585, 13004,
+  14596, 16384, 18390, 20643, 23170 };
+#define RC_QP_MIN 10
+#define RC_QP_MAX 51
+#define RC_STATIC_PARK (1 << 20)
+
+/* QP of picture k from the feedback record it may see (the state after picture k-2). */
+static int rc_frame_qp(const enc_t* e, const struct rcfb* fb, int idr, int rc_mode, int qp_fixed, int64_t target_bits) {
+  const int mbs = e->mbw * e->mbh;
+  const int paint = e->paint_trigger > 0 && !idr && fb->paint;
+  if (rc_mode == 1) return clip3(0, 51, paint ? e->paint_qp : qp_fixed);
+  int q = fb->qp < 0 ? rc_initial_qp(target_bits, mbs) : fb->qp;
+  /* an IDR requested in mid-stream (PLI, resize) is not coded finer than a fresh start with 4x the picture budget would be */
+  if (idr) { int q0 = rc_initial_qp(4 * target_bits, mbs); if (q < q0) q = q0; }
+  if (paint && e->paint_qp < q) q = clip3(0, 51, e->paint_qp);
+  return q;
+}
+
+/* After picture k (its RBSP bit count is known): advance the feedback record.  prev = the record after picture k-1,
+ * used = the record picture k was coded from (after k-2).  Deterministic integer arithmetic: the GPU runs the same code. */
+static void rc_step(const enc_t* e, struct rcfb* out, const struct rcfb* prev, const struct rcfb* used, int64_t bits, int qp_used,
+                    int idr, int coded, int rc_mode, int64_t target) {
+  struct rcfb n = *prev;
+  const int was_paint = e->paint_trigger > 0 && !idr && used->paint;
+  /* paint-over scheduler: count all-skipped pictures; at `paint_trigger` schedule `paint_burst` pictures at the paint-over QP
+   * (each step schedules the picture two ahead); real motion cancels what is left of the burst */
+  if (idr || (coded && !was_paint)) { n.static_run = 0; n.remaining = 0; }
+  else if (!coded) {
+    n.static_run = prev->static_run + 1 > RC_STATIC_PARK ? RC_STATIC_PARK : prev->static_run + 1;
+    if (e->paint_trigger > 0 && n.static_run == e->paint_trigger) n.remaining = e->paint_burst > 0 ? e->paint_burst : 1;
+  }
+  n.paint = n.remaining > 0;
+  if (n.paint) n.remaining--;
+  if (rc_mode == 0) {
+    const int64_t T = target < 1 ? 1 : target;
+    const int mbs = e->mbw * e->mbh;
+    int64_t full = prev->fullness + bits - T;
+    if (full < -4 * T) full = -4 * T;         /* at most four pictures' worth of unspent budget is carried forward */
+    if (full > 64 * T) full = 64 * T;
+    n.fullness = full;
+    int64_t budget = T - full / 16;            /* repay (or spend) the bucket over about 16 pictures */
+    if (budget < T / 2) budget = T / 2;
+    if (budget > 2 * T) budget = 2 * T;
+    const int base = prev->qp < 0 ? rc_initial_qp(T, mbs) : prev->qp;     /* the decision already in flight (for picture k+1) */
+    int q = base;
+    /* X = this picture's complexity, bits x quantiser step (key frames: 0 = unknown).  Decisions compare the last TWO pictures:
+     * a single large picture (a refinement after a QP decrease, a scroll restart) is paid for through the bucket, only a
+     * SUSTAINED overshoot makes the quantiser coarser; and they are absolute (relative to the QP the picture was coded with),
+     * so the two-picture feedback delay does not make the controller react twice to the same overshoot. */
+    n.X = idr ? 0 : bits * RC_QS[qp_used];
+    if (!idr) {
+      const int64_t lim = budget * RC_QS[qp_used];
+      const int64_t lo = prev->X > 0 && prev->X < n.X ? prev->X : n.X, hi = prev->X > n.X ? prev->X : n.X;
+      /* the level the overshoot is judged on: the smaller of the two pictures when one towers over the other (a spike),
+       * their mean otherwise (alternating sizes) */
+      const int64_t eff = hi > 3 * lo ? lo : (lo + hi) / 2;
+      int qt = base;
+      if (eff * 100 > lim * 104) {
+        static const int thr[9] = {104, 119, 133, 150, 168, 189, 238, 300, 378}, stp[9] = {1, 2, 3, 4, 5, 6, 8, 10, 12};
+        int dq = 1;
+        for (int i = 0; i < 9; i++) if (eff * 100 > lim * thr[i]) dq = stp[i];
+        qt = qp_used + dq;
+      } else if (hi * 100 < lim * 88 && full <= 0) {
+        qt = qp_used - ((hi * 2 < lim && full < -2 * T) ? 2 : 1);
+      }
+      q = clip3(base - 2, base + 4, qt);
+    }
+    n.qp = clip3(RC_QP_MIN, RC_QP_MAX, q);
+  }
+  *out = n;
 }
 
 /* ------------------------------------------------------------------ public API */
@@ -1067,7 +1131,7 @@ void* b2v_ref_enc_create(int width, int height, int slice_rows) {
   size_t fb = (size_t)e->cw * e->ch * 3 / 2;
   e->recon[0] = (uint8_t*)calloc(fb, 1); e->recon[1] = (uint8_t*)calloc(fb, 1);
   e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
-  e->rc_qp = -1;
+  e->fb[0].qp = e->fb[1].qp = -1; e->paint_burst = 1;
   e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL;
   write_param_sets(e);
   return e;
@@ -1082,6 +1146,7 @@ int b2v_ref_enc_coded_h(void* h) { return ((enc_t*)h)->ch; }
 const uint8_t* b2v_ref_enc_recon(void* h) { enc_t* e = (enc_t*)h; return e->recon[e->cur]; }
 int b2v_ref_enc_last_qp(void* h) { return ((enc_t*)h)->last_qp; }
 void b2v_ref_enc_set_paintover(void* h, int trigger_frames, int qp) { enc_t* e = (enc_t*)h; e->paint_trigger = trigger_frames; e->paint_qp = qp; }
+void b2v_ref_enc_set_paintover_burst(void* h, int burst_frames) { ((enc_t*)h)->paint_burst = burst_frames > 0 ? burst_frames : 1; }
 /* striped mode: stripe_rows macroblock rows per band (a multiple of slice_rows); 0 = full frame.  Returns the band count or -1. */
 int b2v_ref_enc_set_stripes(void* h, int stripe_rows) {
   enc_t* e = (enc_t*)h;
@@ -1112,12 +1177,9 @@ size_t b2v_ref_enc_max_au(void* h) { enc_t* e = (enc_t*)h; return (size_t)e->mbw
 int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mode, int qp_fixed, int64_t target_bits, uint8_t* out) {
   enc_t* e = (enc_t*)h;
   int mbs = e->mbw * e->mbh;
-  if (rc_mode == 0 && e->rc_qp < 0) e->rc_qp = rc_initial_qp(target_bits, mbs);
-  int qp = rc_mode == 1 ? clip3(0, 51, qp_fixed) : e->rc_qp;
-  if (rc_mode == 1 && e->paint_trigger > 0 && !idr && e->static_run == e->paint_trigger) qp = clip3(0, 51, e->paint_qp);
-  /* CBR: an IDR requested in mid-stream (PLI, resize) is not coded finer than a fresh start with 4x the picture budget
-   * would be, which bounds the latency spike of the key frame */
-  if (rc_mode == 0 && idr) { int q0 = rc_initial_qp(4 * target_bits, mbs); if (qp < q0) qp = q0; }
+  const int k = (int)(e->pic & 1);
+  const struct rcfb used = e->fb[k];                         /* the controller state after picture pic-2 */
+  const int qp = rc_frame_qp(e, &used, idr, rc_mode, qp_fixed, target_bits);
   e->cur ^= 1;
   if (idr) { e->frame_num = 0; }
   /* phase A: analysis + reconstruction.  Intra: macroblocks of a slice are sequential (left/top
@@ -1163,10 +1225,13 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   }
   uint8_t* skip_copy = skip;
   free(tmp); free(lens); free(sbits);
-  { int coded = 0; for (int i = 0; i < mbs; i++) coded |= !skip_copy[i]; int painted = rc_mode == 1 && e->paint_trigger > 0 && !idr && e->static_run == e->paint_trigger;
-    e->static_run = painted ? e->paint_trigger + 1 : (coded || idr) ? 0 : e->static_run + 1; free(skip_copy); }
-  e->last_qp = qp; e->last_bits = (int64_t)o * 8;
-  if (rc_mode == 0) rc_update(e, bits, target_bits, idr);      /* RBSP bits of the slices: known before the byte stream is assembled */
+  { int coded = 0; for (int i = 0; i < mbs; i++) coded |= !skip_copy[i]; free(skip_copy);
+    struct rcfb init; memset(&init, 0, sizeof init); init.qp = -1;
+    const struct rcfb prev = e->pic > 0 ? e->fb[k ^ 1] : init;
+    /* RBSP bits of the slices: known before the byte stream is assembled */
+    /* + 40 bits per slice NAL (start code, NAL header): what the wire carries beyond the RBSP, to a good approximation */
+    rc_step(e, &e->fb[k], &prev, &used, bits + 40LL * e->n_slices, qp, idr, coded, rc_mode, target_bits); }
+  e->last_qp = qp; e->last_bits = (int64_t)o * 8; e->pic++;
   if (idr) e->idr_count++;
   e->frame_num = (e->frame_num + 1) & 255;
   return (int64_t)o;

@@ -398,6 +398,7 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
     fp.qp_fixed = s->qp_fixed;
     fp.paint_trigger = s->cfg.paintover_trigger_frames > 0 ? s->cfg.paintover_trigger_frames : 0;
     fp.paint_qp = s->cfg.paintover_crf;
+    fp.paint_burst = s->cfg.paintover_burst_frames > 0 ? s->cfg.paintover_burst_frames : 1;
     // target bits per frame for the device-side rate controller
     fp.target_bits = (int64_t)((double)s->bitrate_kbps * 1000.0 / (s->fps > 0 ? s->fps : 60.0));
     s->submitted++;

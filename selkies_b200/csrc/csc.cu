@@ -309,6 +309,71 @@ __global__ void __launch_bounds__(256) csc_bgra_nv12_general(CscParams p) {
   *(uint16_t*)(p.out_uv + (size_t)by * p.coded_w + bx * 2) = (uint16_t)(cb | (cr << 8));
 }
 
+// ---- scaled path: fused bilinear scale + CSC through a shared-memory tile -----------------------------------------------------
+// One CTA produces SC_TW x SC_TH output pixels (one thread per 2x2 block: the chroma sample needs all four).  The source
+// footprint of the tile — tx[first].i0 .. tx[last].i1 by ty[first].i0 .. ty[last].i1, a few KB whatever the scale factor — is
+// staged in shared memory with 16-byte loads; every tap is then a shared-memory read.  The arithmetic is the spec's (oracle/
+// csc_ref.c fetch_bgr): per channel top/bottom horizontal blends at full precision (B and R ride in the two 16-bit halves of one
+// word: 255*256 fits), one vertical blend, one rounding.  Roofline: 4 B per source pixel read + 1.5 B per output pixel written.
+constexpr int SC_TW = 64, SC_TH = 8, SC_THREADS = (SC_TW / 2) * (SC_TH / 2);
+
+__device__ __forceinline__ void blend_px(const uint32_t* r0, const uint32_t* r1, int x0, int x1, int fx, int fy, int& B, int& G, int& R) {
+  const uint32_t p00 = r0[x0], p01 = r0[x1], p10 = r1[x0], p11 = r1[x1];
+  const uint32_t M = 0x00ff00ffu;
+  const uint32_t wx1 = (uint32_t)fx, wx0 = 256u - wx1;
+  const uint32_t tbr = (p00 & M) * wx0 + (p01 & M) * wx1, bbr = (p10 & M) * wx0 + (p11 & M) * wx1;        // [B | R << 16], each <= 65280
+  const uint32_t tg = ((p00 >> 8) & 255u) * wx0 + ((p01 >> 8) & 255u) * wx1, bg = ((p10 >> 8) & 255u) * wx0 + ((p11 >> 8) & 255u) * wx1;
+  const uint32_t wy1 = (uint32_t)fy, wy0 = 256u - wy1;
+  B = (int)(((tbr & 0xffffu) * wy0 + (bbr & 0xffffu) * wy1 + (1u << 15)) >> 16);
+  R = (int)(((tbr >> 16) * wy0 + (bbr >> 16) * wy1 + (1u << 15)) >> 16);
+  G = (int)((tg * wy0 + bg * wy1 + (1u << 15)) >> 16);
+}
+
+__global__ void __launch_bounds__(SC_THREADS) csc_bgra_nv12_scaled(CscParams p, int fw_cap, int fh_cap) {
+  extern __shared__ __align__(16) uint32_t sc_tile[];            // fh_cap rows of fw_cap pixels (fw_cap % 4 == 0)
+  const int tid = threadIdx.x;
+  const int ox0 = blockIdx.x * SC_TW, oy0 = blockIdx.y * SC_TH;
+  // footprint of this tile in the source (output coordinates beyond the visible picture replicate its last row / column)
+  const int xf = min(ox0, p.dst_w - 1), xl = min(ox0 + SC_TW - 1, p.dst_w - 1);
+  const int yf = min(oy0, p.dst_h - 1), yl = min(oy0 + SC_TH - 1, p.dst_h - 1);
+  const int xs0 = p.tx[xf].i0 & ~3, xs1 = p.tx[xl].i1, ys0 = p.ty[yf].i0, ys1 = p.ty[yl].i1;
+  const int fw4 = (xs1 - xs0 + 4) >> 2, fh = ys1 - ys0 + 1;      // quads per row, rows
+  for (int i = tid; i < fh * fw4; i += SC_THREADS) {
+    const int r = i / fw4, c = i - r * fw4, sx = xs0 + 4 * c;
+    const uint8_t* g = p.src + (size_t)(ys0 + r) * p.src_stride + (size_t)sx * 4;
+    uint4 v;
+    if (sx + 3 < p.src_w) v = ld_stream(g);
+    else {                                                      // last quad of a row whose width is not a multiple of 4
+      v.x = *reinterpret_cast<const uint32_t*>(g);
+      v.y = sx + 1 < p.src_w ? *reinterpret_cast<const uint32_t*>(g + 4) : 0u;
+      v.z = sx + 2 < p.src_w ? *reinterpret_cast<const uint32_t*>(g + 8) : 0u;
+      v.w = 0u;
+    }
+    *reinterpret_cast<uint4*>(&sc_tile[r * fw_cap + 4 * c]) = v;
+  }
+  (void)fh_cap;
+  __syncthreads();
+  const int bx = tid % (SC_TW / 2), by = tid / (SC_TW / 2);
+  const int ox = ox0 + 2 * bx, oy = oy0 + 2 * by;
+  if (ox >= p.coded_w || oy >= p.coded_h) return;
+  int sb = 0, sg = 0, sr = 0;
+  unsigned yy[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = min(ox + (k & 1), p.dst_w - 1), y = min(oy + (k >> 1), p.dst_h - 1);
+    const Tap ax = p.tx[x], ay = p.ty[y];
+    int B, G, R;
+    blend_px(&sc_tile[(ay.i0 - ys0) * fw_cap], &sc_tile[(ay.i1 - ys0) * fw_cap], ax.i0 - xs0, ax.i1 - xs0, ax.f, ay.f, B, G, R);
+    yy[k] = (unsigned)(KYR * R + KYG * G + KYB * B + Y_SEED) >> 14;
+    sb += B; sg += G; sr += R;
+  }
+  const unsigned cb = (unsigned)(KUR * sr + KUG * sg + KUB * sb + C_SEED) >> 16;
+  const unsigned cr = (unsigned)(KVR * sr + KVG * sg + KVB * sb + C_SEED) >> 16;
+  *reinterpret_cast<uint16_t*>(p.out_y + (size_t)oy * p.coded_w + ox) = (uint16_t)(yy[0] | (yy[1] << 8));
+  *reinterpret_cast<uint16_t*>(p.out_y + (size_t)(oy + 1) * p.coded_w + ox) = (uint16_t)(yy[2] | (yy[3] << 8));
+  *reinterpret_cast<uint16_t*>(p.out_uv + (size_t)(oy >> 1) * p.coded_w + ox) = (uint16_t)(cb | (cr << 8));
+}
+
 // host side ---------------------------------------------------------------------------------
 void make_taps_host(Tap* t, int dn, int sn) {
   for (int d = 0; d < dn; d++) {
@@ -322,7 +387,7 @@ void make_taps_host(Tap* t, int dn, int sn) {
   }
 }
 
-static int g_csc_u = 2, g_csc_block = 160, g_csc_rows_per_block = 0, g_csc_tma = 0, g_csc_tma_ctas_per_sm = 2, g_csc_tma_stages = 4, g_csc_evict_first = 0;
+static int g_csc_u = 2, g_csc_block = 160, g_csc_rows_per_block = 0, g_csc_tma = 0, g_csc_tma_ctas_per_sm = 2, g_csc_tma_stages = 4, g_csc_evict_first = 0, g_csc_scaled_tiled = 1;
 static void csc_env_once() {      // experiment switch, read once: B2V_CSC = ldg | ldg_ef | tma
   static bool done = false;
   if (done) return;
@@ -332,6 +397,7 @@ static void csc_env_once() {      // experiment switch, read once: B2V_CSC = ldg
   if (!strcmp(e, "ldg")) { g_csc_tma = 0; g_csc_evict_first = 0; }
   else if (!strcmp(e, "ldg_ef")) { g_csc_tma = 0; g_csc_evict_first = 1; }
   else if (!strcmp(e, "tma")) { g_csc_tma = 1; }
+  else if (!strcmp(e, "scaled_general")) { g_csc_scaled_tiled = 0; }
 }
 extern "C" void b2v_tune_csc(int u, int block, int gy) {   // bench/tuning hook (not part of the drop-in ABI)
   if (u > 0) g_csc_u = u;
@@ -417,6 +483,19 @@ int launch_csc(const CscParams& p, int sm_count, cudaStream_t st) {
       }
     }
   } else {
+    // scaled: the tiled kernel when the tile's source footprint fits shared memory (any sane scale factor), else the general one
+    if (p.tx && p.ty && g_csc_scaled_tiled && (p.src_stride % 16) == 0 && ((uintptr_t)p.src % 16) == 0) {
+      const long long fw = ((long long)SC_TW * p.src_w + p.dst_w - 1) / p.dst_w + 8, fh = ((long long)SC_TH * p.src_h + p.dst_h - 1) / p.dst_h + 3;
+      const int fw_cap = (int)((fw + 3) & ~3LL), fh_cap = (int)fh;
+      const long long smem = (long long)fw_cap * fh_cap * 4;
+      if (smem <= 96 * 1024) {
+        static int attr = 0;
+        if (smem > 48 * 1024 && smem > attr) { cudaFuncSetAttribute(csc_bgra_nv12_scaled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = (int)smem; }
+        dim3 grid((p.coded_w + SC_TW - 1) / SC_TW, (p.coded_h + SC_TH - 1) / SC_TH);
+        csc_bgra_nv12_scaled<<<grid, SC_THREADS, (size_t)smem, st>>>(p, fw_cap, fh_cap);
+        return 1;
+      }
+    }
     dim3 block(32, 8);
     dim3 grid((p.coded_w / 2 + 31) / 32, (p.coded_h / 2 + 7) / 8);
     csc_bgra_nv12_general<<<grid, block, 0, st>>>(p);

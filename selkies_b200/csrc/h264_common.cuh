@@ -24,29 +24,45 @@ struct __align__(8) MbInfo {
   uint8_t cbp;             // luma bits 0..3 | chroma << 4
 };
 
-struct RcState {
-  int32_t qp;              // QP for the next CBR picture (-1 = not initialised)
-  int32_t pad;
-  long long fullness;
-  int32_t last_qp;
-  int32_t frames;
+// Feedback record of the rate controller / paint-over scheduler.  fb[k & 1] is written after picture k (rc_step, last block of
+// its slice scan); picture k is CODED from fb[k & 1] as it stood before that — the state after picture k-2 — because the entropy
+// coding of picture k-1, where its size becomes known, overlaps the analysis of picture k on another stream.  The two records
+// alternate, so nothing a running kernel reads is ever written concurrently.  Mirrors oracle/h264_ref.c struct rcfb / rc_step.
+struct RcFb {
+  int32_t qp;              // CBR: QP decided for the picture two ahead (-1 = not initialised)
   int32_t static_run;      // consecutive pictures in which every macroblock was skipped
-  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by rc_step (last slice-scan block)
-  long long pic_bits;      // RBSP bits of the picture just scanned (rate-control step -> AuHeader.total_bits)
-  int32_t scan_done;       // slice-scan blocks that have finished this picture (the last one runs the rate-control step)
-  int32_t pad3;
+  int32_t remaining;       // paint-over pictures still to schedule
+  int32_t paint;           // the picture that reads this record is coded at the paint-over QP
+  long long fullness;      // leaky bucket: bits spent above the target
+  long long X;             // complexity of the picture just coded: bits x quantiser step (0 = key frame / unknown)
 };
+struct RcState {
+  RcFb fb[2];
+  int32_t last_qp;         // QP of the picture whose slice scan ran last (read by its pack kernel)
+  int32_t frames;
+  int32_t pic_coded;       // set by the slice scan when a slice holds a non-skipped macroblock; consumed and cleared by rc_step (last slice-scan block)
+  int32_t scan_done;       // slice-scan blocks that have finished this picture (the last one runs the rate-control step)
+  long long pic_bits;      // RBSP bits of the picture just scanned (rate-control step -> AuHeader.total_bits)
+};
+constexpr int RC_QP_MIN = 10, RC_QP_MAX = 51, RC_STATIC_PARK = 1 << 20;
+// quantiser step in Q6 (64 * 2^(qp/6)); complexity X = bits * rc_qs[qp]
+__device__ const int32_t rc_qs[52] = {
+  64, 72, 81, 91, 102, 114, 128, 144, 161, 181, 203, 228, 256, 287, 323, 362, 406, 456, 512, 575, 645, 724, 813, 912, 1024, 1149,
+  1290, 1448, 1625, 1825, 2048, 2299, 2580, 2896, 3251, 3649, 4096, 4598, 5161, 5793, 6502, 7298, 8192, 9195, 10321, 11585, 13004,
+  14596, 16384, 18390, 20643, 23170};
 
 struct FrameCtx {          // everything a kernel needs about the picture being coded
   int cw, ch, mbw, mbh, slice_rows, n_slices;
   int idr, rc_mode, qp_fixed;
-  int paint_trigger, paint_qp;   // CQP mode paint-over: one refinement picture after `paint_trigger` all-skipped pictures (0 = off)
+  int paint_trigger, paint_qp, paint_burst;   // paint-over: `paint_burst` refinement pictures after `paint_trigger` all-skipped pictures (0 = off)
+  int pic;                 // picture counter of this encoder (parity selects the feedback record and the double-buffered side data)
   long long target_bits;
   int frame_num, idr_pic_id;
   const uint8_t* cur;      // NV12 coded size
   const uint8_t* ref;      // previous reconstruction (NV12)
   uint8_t* recon;          // reconstruction being written
-  MbInfo* mbinfo;
+  MbInfo* mbinfo;          // this picture's records (double-buffered: the entropy kernels of picture k read them while picture k+1 is analysed)
+  const MbInfo* mbinfo_prev;   // the previous picture's records (temporal motion predictor)
   uint8_t* i4modes;        // [mbs][16] Intra4x4PredMode per block (raster), valid for MB_I4
   int16_t* coef;           // [mbs][27][16]
   uint8_t* nnz;            // [mbs][32]: 0..15 luma raster, 16..19 Cb, 20..23 Cr
@@ -81,16 +97,17 @@ __device__ __forceinline__ int rc_initial_qp(long long target_bits, int mbs) {
   long long per_mb = target_bits / (mbs > 0 ? mbs : 1);
   return per_mb >= 400 ? 22 : per_mb >= 200 ? 26 : per_mb >= 100 ? 30 : per_mb >= 50 ? 34 : per_mb >= 25 ? 38 : 42;
 }
+// QP of this picture, from the feedback record it may see (the state after picture pic-2).  oracle/h264_ref.c rc_frame_qp.
 __device__ __forceinline__ int frame_qp(const FrameCtx& f) {
-  if (f.rc_mode == 1) {
-    // paint-over: the scene has been static for `paint_trigger` pictures -> one picture at the (finer) paint-over QP
-    if (f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger) return clip3i(0, 51, f.paint_qp);
-    return clip3i(0, 51, f.qp_fixed);
-  }
-  int q = f.rc->qp;
+  const RcFb& fb = f.rc->fb[f.pic & 1];
+  // paint-over: the scene has been static for `paint_trigger` pictures -> `paint_burst` pictures at the (finer) paint-over QP
+  const bool paint = f.paint_trigger > 0 && !f.idr && fb.paint;
+  if (f.rc_mode == 1) return clip3i(0, 51, paint ? f.paint_qp : f.qp_fixed);
+  int q = fb.qp;
   if (q < 0) q = rc_initial_qp(f.target_bits, f.mbw * f.mbh);
   // an IDR in mid-stream is not coded finer than a fresh start with 4x the picture budget would be (bounds the key-frame burst)
   if (f.idr) q = max(q, rc_initial_qp(4 * f.target_bits, f.mbw * f.mbh));
+  if (paint && f.paint_qp < q) q = clip3i(0, 51, f.paint_qp);
   return q;
 }
 __device__ __forceinline__ bool top_in_slice(const FrameCtx& f, int mby) { return (mby % f.slice_rows) != 0; }
@@ -150,12 +167,25 @@ __device__ __forceinline__ constexpr int zz(int k) {
 }
 __device__ __forceinline__ constexpr int pcls(int r) { return (((r & 3) | (r >> 2)) & 1) == 0 ? 0 : (((r & 3) & (r >> 2)) & 1) ? 1 : 2; }
 
-// Forward transform + quantise one 4x4 residual block.  lv[k]: scan-order levels.  When dc_separate the
+// True when every (AC, if DC_SEPARATE) coefficient of the transformed block w quantises to level 0: quant1() gives 0 exactly when
+// |w|*MF + f < 2^qbits, and MF only depends on the position class, so three maxima decide it — a third of the cost of quantising
+// the sixteen coefficients one by one.  Exact, not a heuristic: the levels it predicts to be zero ARE zero.
+template <bool DC_SEPARATE>
+__device__ __forceinline__ bool block_quantises_to_zero(const int w[16], const QuantParams& q) {
+  int m[3] = {0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    if (DC_SEPARATE && r == 0) continue;
+    m[pcls(r)] = max(m[pcls(r)], abs(w[r]));
+  }
+  const int lim = (1 << q.qbits) - q.f;
+  return m[0] * q.mf[0] < lim && m[1] * q.mf[1] < lim && m[2] * q.mf[2] < lim;
+}
+
+// Quantise one transformed 4x4 block.  lv[k]: scan-order levels.  When dc_separate the
 // DC coefficient is returned un-quantised in w_dc and lv[0] = 0.  Returns the number of non-zero levels.
 template <bool DC_SEPARATE>
-__device__ __forceinline__ int tq_block(const int res[16], const QuantParams& q, int lv[16], int& w_dc) {
-  int w[16];
-  fwd4x4(res, w);
+__device__ __forceinline__ int quant_block(const int w[16], const QuantParams& q, int lv[16], int& w_dc) {
   int n = 0;
 #pragma unroll
   for (int k = 0; k < 16; k++) {
@@ -164,6 +194,12 @@ __device__ __forceinline__ int tq_block(const int res[16], const QuantParams& q,
     n += lv[k] != 0;
   }
   return n;
+}
+template <bool DC_SEPARATE>
+__device__ __forceinline__ int tq_block(const int res[16], const QuantParams& q, int lv[16], int& w_dc) {
+  int w[16];
+  fwd4x4(res, w);
+  return quant_block<DC_SEPARATE>(w, q, lv, w_dc);
 }
 // dequantise + inverse transform; when USE_DC the (already dequantised) dc replaces d[0]
 template <bool USE_DC>
@@ -207,7 +243,7 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
   const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
   const int qpc = chroma_qp_tab[qp];
   const QuantParams q = make_quant(is_chroma ? qpc : qp, INTRA16);
-  int lv[16], w_dc = 0, n = 0, bx = 0, by = 0, comp = 0;
+  int lv[16], w[16], w_dc = 0, n = 0, bx = 0, by = 0, comp = 0;
   if (is_luma) {
     bx = blk_x[lane] * 4; by = blk_y[lane] * 4;
     int res[16];
@@ -218,7 +254,7 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
 #pragma unroll
       for (int j = 0; j < 4; j++) res[4 * i + j] = (int)((c >> (8 * j)) & 255) - (int)((p >> (8 * j)) & 255);
     }
-    n = INTRA16 ? tq_block<true>(res, q, lv, w_dc) : tq_block<false>(res, q, lv, w_dc);
+    fwd4x4(res, w);
   } else if (is_chroma) {
     comp = (lane - 16) >> 2;
     int b = (lane - 16) & 3;
@@ -228,11 +264,40 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
     for (int i = 0; i < 4; i++)
 #pragma unroll
       for (int j = 0; j < 4; j++) res[4 * i + j] = (int)t.cur_uv[by + i][(bx + j) * 2 + comp] - (int)t.pred_uv[by + i][(bx + j) * 2 + comp];
-    n = tq_block<true>(res, q, lv, w_dc);
+    fwd4x4(res, w);
   } else {
 #pragma unroll
-    for (int k = 0; k < 16; k++) lv[k] = 0;
+    for (int k = 0; k < 16; k++) { lv[k] = 0; w[k] = 0; }
   }
+  // ---- inter macroblock in which NOTHING survives quantisation (the common case on a desktop: static regions, and scrolled
+  // regions whose prediction repeats last picture's residual): decided from the transformed coefficients with three maxima per
+  // block + the chroma DC Hadamard — no level is computed.  The result is exactly what the full path below would produce
+  // (every level 0 -> reconstruction = prediction, nothing stored, cbp 0), so the oracle needs no counterpart. ----
+  if (!INTRA16) {
+    bool z = true;
+    if (is_luma) z = block_quantises_to_zero<false>(w, q);
+    else if (is_chroma) z = block_quantises_to_zero<true>(w, q);
+    {
+      const int b = (lane - 16) & 3, d = is_chroma ? w[0] : 0;
+      const int o1 = __shfl_xor_sync(FULL, d, 1), o2 = __shfl_xor_sync(FULL, d, 2), o3 = __shfl_xor_sync(FULL, d, 3);
+      // 2x2 Hadamard output b of this component's four DC coefficients (lane b holds d_b; d_(b^x) arrives by xor-shuffle)
+      const int s1 = (b & 1) ? -1 : 1, s2 = (b & 2) ? -1 : 1;
+      const int tk = d + s1 * o1 + s2 * o2 + s1 * s2 * o3;      // == the tk the full path computes (sign of the whole row is irrelevant for |tk|)
+      if (is_chroma) z = z && (abs(tk) * q.mf[0] + 2 * q.f < (1 << (q.qbits + 1)));
+    }
+    if (__all_sync(FULL, z)) {
+      if (is_luma) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) *reinterpret_cast<uint32_t*>(&t.rec_y[by + i][bx]) = *reinterpret_cast<const uint32_t*>(&t.pred_y[by + i][bx]);
+      }
+      reinterpret_cast<uint32_t*>(&t.rec_uv[0][0])[lane] = reinterpret_cast<const uint32_t*>(&t.pred_uv[0][0])[lane];
+      if (lane < 24) nnz_mb[lane] = 0;
+      luma_bits = 0; chroma_bits = 0;
+      return 0;
+    }
+  }
+  if (is_luma) n = INTRA16 ? quant_block<true>(w, q, lv, w_dc) : quant_block<false>(w, q, lv, w_dc);
+  else if (is_chroma) n = quant_block<true>(w, q, lv, w_dc);
   // ---- coefficient decimation of inter luma (oracle/h264_ref.c encode_inter_mb): block score = 9 if any
   // |level| > 1, else sum over its +-1 levels of {3,2,2,1,1,1,0..}[zeros just below]; an 8x8 quadrant (lanes 4k..4k+3) scoring
   // < 4 is zeroed, the whole luma when the macroblock scores < 6 ------------------------------------------------------

@@ -22,10 +22,12 @@ struct Encoder {
   int mbw = 0, mbh = 0, n_slices = 0;
   uint8_t* recon[2] = {nullptr, nullptr};
   int cur = 0;
-  MbInfo* mbinfo = nullptr;
-  uint8_t* i4modes = nullptr;
-  int16_t* coef = nullptr;
-  uint8_t* nnz = nullptr;
+  // side data the analysis kernels write and the entropy kernels read: double-buffered by picture parity, so the entropy coding
+  // of picture k (packing stream) overlaps the analysis of picture k+1 (main stream)
+  MbInfo* mbinfo[2] = {nullptr, nullptr};
+  uint8_t* i4modes[2] = {nullptr, nullptr};
+  int16_t* coef[2] = {nullptr, nullptr};
+  uint8_t* nnz[2] = {nullptr, nullptr};
   long long* mb_off = nullptr; int* mb_run = nullptr;
   uint32_t *mb_words = nullptr, *mb_nbits = nullptr, *slice_buf = nullptr, *slice_size = nullptr, *slice_rbsp = nullptr;
   long long* slice_bits = nullptr;
@@ -36,7 +38,8 @@ struct Encoder {
   uint8_t* param_sets = nullptr; int param_len = 0, param_len_last = 0;
   int band_rows = 0, n_bands = 1, striped = 0, au_data_off = (int)sizeof(AuHeader);
   int *band_fn = nullptr, *band_coded = nullptr;
-  cudaEvent_t ev_scanned = nullptr, ev_packed = nullptr;   // two-stream schedule: scan+rc done on the main stream / AU packed on st_pack
+  cudaEvent_t ev_analysed[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};   // two-stream schedule, by picture parity
+  long long pic = 0;       // pictures encoded so far
   size_t au_cap = 0;
   int frame_num = 0, idr_count = 0;
   bool have_ref = false;
@@ -136,13 +139,16 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMalloc((void**)&e->recon[1], fb));
   ECK(cudaMemset(e->recon[0], 0, fb));
   ECK(cudaMemset(e->recon[1], 0, fb));
-  ECK(cudaMalloc((void**)&e->mbinfo, mbs * sizeof(MbInfo)));
-  ECK(cudaMalloc((void**)&e->i4modes, mbs * 16));
-  ECK(cudaMemset(e->i4modes, 2, mbs * 16));
-  ECK(cudaMalloc((void**)&e->coef, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
-  ECK(cudaMemset(e->coef, 0, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
-  ECK(cudaMalloc((void**)&e->nnz, mbs * 32));
-  ECK(cudaMemset(e->nnz, 0, mbs * 32));
+  for (int b = 0; b < 2; b++) {
+    ECK(cudaMalloc((void**)&e->mbinfo[b], mbs * sizeof(MbInfo)));
+    ECK(cudaMemset(e->mbinfo[b], 0, mbs * sizeof(MbInfo)));
+    ECK(cudaMalloc((void**)&e->i4modes[b], mbs * 16));
+    ECK(cudaMemset(e->i4modes[b], 2, mbs * 16));
+    ECK(cudaMalloc((void**)&e->coef[b], mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
+    ECK(cudaMemset(e->coef[b], 0, mbs * COEF_BLOCKS * 16 * sizeof(int16_t)));
+    ECK(cudaMalloc((void**)&e->nnz[b], mbs * 32));
+    ECK(cudaMemset(e->nnz[b], 0, mbs * 32));
+  }
   ECK(cudaMalloc((void**)&e->mb_words, mbs * MB_WORDS * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->mb_nbits, mbs * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->mb_off, mbs * sizeof(long long)));
@@ -157,7 +163,7 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMalloc((void**)&e->overflow, sizeof(int)));
   ECK(cudaMemset(e->overflow, 0, sizeof(int)));
   ECK(cudaMalloc((void**)&e->rc, sizeof(RcState)));
-  RcState rc0{}; rc0.qp = -1;
+  RcState rc0{}; rc0.fb[0].qp = rc0.fb[1].qp = -1;
   ECK(cudaMemcpy(e->rc, &rc0, sizeof rc0, cudaMemcpyHostToDevice));
   // bands: full-frame coding is one band of mbh rows; striped mode gives every band its own SPS (height = the band's)
   const int crop_b = (cfg->coded_h - cfg->height) / 2;
@@ -179,8 +185,10 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMemset(e->band_fn, 0, e->n_bands * sizeof(int)));
   ECK(cudaMalloc((void**)&e->band_coded, e->n_bands * sizeof(int)));
   ECK(cudaMemset(e->band_coded, 0, e->n_bands * sizeof(int)));
-  ECK(cudaEventCreateWithFlags(&e->ev_scanned, cudaEventDisableTiming));
-  ECK(cudaEventCreateWithFlags(&e->ev_packed, cudaEventDisableTiming));
+  for (int b = 0; b < 2; b++) {
+    ECK(cudaEventCreateWithFlags(&e->ev_analysed[b], cudaEventDisableTiming));
+    ECK(cudaEventCreateWithFlags(&e->ev_packed[b], cudaEventDisableTiming));
+  }
   e->au_cap = (size_t)e->au_data_off + (size_t)e->n_bands * (e->param_len + e->param_len_last) + (size_t)e->n_slices * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
   *out = e;
   return 0;
@@ -188,11 +196,14 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
 
 void encoder_destroy(Encoder* e) {
   if (!e) return;
-  void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo, e->coef, e->nnz, e->mb_words, e->mb_nbits, e->slice_buf, e->slice_size,
-                  e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes, e->band_fn, e->band_coded};
+  void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo[0], e->mbinfo[1], e->coef[0], e->coef[1], e->nnz[0], e->nnz[1], e->mb_words, e->mb_nbits, e->slice_buf,
+                  e->slice_size, e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes[0],
+                  e->i4modes[1], e->band_fn, e->band_coded};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (e->ev_scanned) cudaEventDestroy(e->ev_scanned);
-  if (e->ev_packed) cudaEventDestroy(e->ev_packed);
+  for (int b = 0; b < 2; b++) {
+    if (e->ev_analysed[b]) cudaEventDestroy(e->ev_analysed[b]);
+    if (e->ev_packed[b]) cudaEventDestroy(e->ev_packed[b]);
+  }
   delete e;
 }
 
@@ -204,45 +215,52 @@ const uint8_t* encoder_recon(const Encoder* e) { return e->recon[e->cur]; }
 int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   const bool idr = p->idr || !e->have_ref;
   e->cur ^= 1;
+  const int par = (int)(e->pic & 1);          // parity of this picture: feedback record, side-data buffers, events
   if (idr) e->frame_num = 0;
   FrameCtx f{};
   f.cw = e->cfg.coded_w; f.ch = e->cfg.coded_h; f.mbw = e->mbw; f.mbh = e->mbh;
   f.slice_rows = e->cfg.slice_rows; f.n_slices = e->n_slices;
   f.idr = idr; f.rc_mode = p->rc_mode; f.qp_fixed = p->qp_fixed; f.target_bits = p->target_bits;
-  f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count;
+  f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count; f.pic = (int)(e->pic & 0x7fffffff);
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
-  f.mbinfo = e->mbinfo; f.i4modes = e->i4modes; f.coef = e->coef; f.nnz = e->nnz; f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
+  f.mbinfo = e->mbinfo[par]; f.mbinfo_prev = e->mbinfo[par ^ 1]; f.i4modes = e->i4modes[par]; f.coef = e->coef[par]; f.nnz = e->nnz[par];
+  f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
   f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
-  f.slice_bits = e->slice_bits; f.paint_trigger = p->paint_trigger; f.paint_qp = p->paint_qp; f.progress = e->progress; f.rc = e->rc;
+  f.slice_bits = e->slice_bits; f.paint_trigger = p->paint_trigger; f.paint_qp = p->paint_qp; f.paint_burst = p->paint_burst; f.progress = e->progress; f.rc = e->rc;
   f.band_rows = e->band_rows; f.n_bands = e->n_bands; f.striped = e->striped; f.param_len_last = e->param_len_last;
   f.band_fn = e->band_fn; f.band_coded = e->band_coded; f.au_data_off = e->au_data_off;
   f.param_sets = e->param_sets; f.param_len = e->param_len; f.csc_ts = p->csc_ts; f.au = p->au; f.overflow = e->overflow;
   int n = 0;
+  // Two-stream schedule (no per-stage events requested): ANALYSIS of picture k on `st` (CSC before it, by the caller), ENTROPY
+  // coding of picture k (CAVLC, slice scan + rate-control step, copy, emulation-prevention count, pack) on `st_pack`, overlapping
+  // the analysis of picture k+1.  What makes that legal:
+  //  * the side data the two halves share (MbInfo, levels, nnz, Intra4x4 modes) is double-buffered by picture parity;
+  //  * the rate controller feeds back two pictures late: picture k reads the record left by picture k-2 (RcFb), which the scan
+  //    of picture k-1 — possibly still running — never touches;
+  //  * the analysis of picture k waits for the pack of picture k-2: that releases this parity's side data, the reconstruction
+  //    buffer it is about to overwrite (the pack's copy kernel reads I_PCM samples from it) and the record of k-2.
+  const bool overlap = p->st_pack != nullptr && p->ev == nullptr;
+  if (overlap) cudaStreamWaitEvent(st, e->ev_packed[par], 0);           // pack of picture k-2 (no-op before the first two)
   n += idr ? launch_intra(f, st) : launch_inter(f, st);
   if (p->ev) cudaEventRecord(p->ev[2], st);
-  // Two-stream schedule (no per-stage events requested): the byte-stream assembly of picture N (copy, emulation-prevention
-  // count, pack) runs on st_pack while st already analyses picture N+1.  What those kernels read is not written by the
-  // analysis kernels (bit strings, slice scratch, the reconstruction of N — a read-only reference for N+1); the entropy
-  // kernels of N+1, which do rewrite it, wait for ev_packed.  The rate controller has already advanced in k_slice_scan (rc_step).
-  const bool overlap = p->st_pack != nullptr && p->ev == nullptr;
-  if (overlap) cudaStreamWaitEvent(st, e->ev_packed, 0);          // the previous picture's pack (no-op before the first)
-  n += launch_cavlc(f, st);
-  if (p->ev) cudaEventRecord(p->ev[3], st);
-  n += launch_slice_scan(f, st);
   cudaStream_t sp = st;
   if (overlap) {
     sp = p->st_pack;
-    cudaEventRecord(e->ev_scanned, st);
-    cudaStreamWaitEvent(sp, e->ev_scanned, 0);
+    cudaEventRecord(e->ev_analysed[par], st);
+    cudaStreamWaitEvent(sp, e->ev_analysed[par], 0);
   }
+  n += launch_cavlc(f, sp);
+  if (p->ev) cudaEventRecord(p->ev[3], st);
+  n += launch_slice_scan(f, sp);
   n += launch_slice_copy_ep(f, sp);
   if (p->ev) cudaEventRecord(p->ev[4], st);
   n += launch_pack_cap(f, (long long)e->au_cap, sp);
   if (p->ev) cudaEventRecord(p->ev[5], st);
-  if (overlap) cudaEventRecord(e->ev_packed, sp);
+  if (overlap) cudaEventRecord(e->ev_packed[par], sp);
   if (idr) e->idr_count++;
   e->frame_num = (e->frame_num + 1) & 255;
   e->have_ref = true;
+  e->pic++;
   return n;
 }
 

@@ -41,11 +41,11 @@ struct EncodeFrameParams {
   int idr;
   int rc_mode;             // B2V_RC_CBR | B2V_RC_CQP
   int qp_fixed;
-  int paint_trigger, paint_qp;   // CQP paint-over (0 = off)
+  int paint_trigger, paint_qp, paint_burst;   // paint-over: `paint_burst` pictures at paint_qp after `paint_trigger` all-skipped pictures (0 = off)
   int64_t target_bits;     // per frame, CBR
   cudaEvent_t* ev;         // null, or 8 timing events: encoder records ev[2..5] after each stage (forces the serial schedule)
-  cudaStream_t st_pack;    // null = everything on `st`; else the byte-stream assembly of this picture (k_slice_copy/ep, k_pack_au)
-                           // runs here, overlapping the analysis of the next picture on `st`.  The access unit is complete on st_pack.
+  cudaStream_t st_pack;    // null = everything on `st`; else the entropy coding of this picture (k_cavlc_mb ... k_pack_au) runs here,
+                           // overlapping the analysis of the next picture on `st`.  The access unit is complete on st_pack.
   const unsigned long long* csc_ts;   // null, or the CSC launch's device stamps to forward in the AuHeader
 };
 

@@ -227,36 +227,57 @@ __device__ __forceinline__ void or_word(uint32_t* out, long long bitpos, uint32_
   else { atomicOr(&out[wi], v >> o); atomicOr(&out[wi + 1], v << (32 - o)); }
 }
 
-__device__ __forceinline__ void rc_update_dev(RcState* rc, long long bits, long long target, int idr, int qp_used) {
-  if (target < 1) target = 1;
-  const long long ref = idr ? 4 * target : target;
-  const long long r = bits * 16 / ref;
-  int dq = r >= 48 ? 4 : r >= 32 ? 3 : r >= 24 ? 2 : r >= 19 ? 1 : r <= 1 ? -4 : r <= 4 ? -2 : r <= 13 ? -1 : 0;
-  long long full = rc->fullness + bits - target;
-  if (full < -4 * target) full = -4 * target;
-  if (full > 16 * target) full = 16 * target;
-  // bucket over-full (typically after a key frame): raise the QP — unless this picture used under a quarter of its budget
-  // (static scene: the debt is being repaid anyway); then at most one step finer per picture
-  if (full > 4 * target) { if (r > 4) { if (dq < 1) dq = 1; } else if (dq < -1) dq = -1; }
-  if (full < -2 * target && dq > -1) dq = -1;
-  rc->fullness = full;
-  rc->qp = clip3i(10, 48, qp_used + dq);
-}
-
-// ---- rate-control step, run by the LAST slice-scan block of the picture (thread 0).  The picture's RBSP bit count is known
-// at that point (the byte stream adds start codes and emulation prevention, which the controller does not need), so the rate
-// controller, the paint-over counter and the per-picture flags advance here and the next picture's analysis can start while
-// this picture's byte stream is still being assembled (k_slice_copy / k_slice_ep / k_pack_au on the packing stream).
-__device__ __forceinline__ void rc_step(const FrameCtx& f, int qp, long long bits) {
-  // the controller evolves the running QP, not the (possibly raised) QP this picture was coded with
-  const int run_qp = f.rc->qp < 0 ? rc_initial_qp(f.target_bits, f.mbw * f.mbh) : f.rc->qp;
-  if (f.rc_mode == 0) rc_update_dev(f.rc, bits, f.target_bits, f.idr, run_qp);
-  f.rc->last_qp = qp; f.rc->frames++; f.rc->pic_bits = bits;
-  const int coded = __ldcg(&f.rc->pic_coded);      // stored by other blocks of this launch: read through L2
-  f.rc->pic_coded = 0;
-  // a paint-over picture parks the counter above the trigger, so the scene is refined once until something moves again
-  const bool painted = f.rc_mode == 1 && f.paint_trigger > 0 && !f.idr && f.rc->static_run == f.paint_trigger;
-  f.rc->static_run = painted ? f.paint_trigger + 1 : (coded || f.idr) ? 0 : f.rc->static_run + 1;
+// ---- rate-control / paint-over step, run by the LAST slice-scan block of the picture (thread 0).  The picture's RBSP bit count
+// is known at that point (the byte stream adds emulation prevention, which the controller does not need), so the feedback
+// record advances here while the rest of the byte-stream assembly is still to come.  Same integer arithmetic as
+// oracle/h264_ref.c rc_step: prev = the record after picture k-1, used = the record picture k was coded from (after k-2).
+__device__ __forceinline__ void rc_step(const FrameCtx& f, int qp_used, long long rbsp_bits) {
+  RcState* rc = f.rc;
+  const RcFb prev = rc->fb[(f.pic & 1) ^ 1], used = rc->fb[f.pic & 1];
+  const int coded = __ldcg(&rc->pic_coded);      // stored by other blocks of this launch: read through L2
+  rc->pic_coded = 0;
+  rc->last_qp = qp_used; rc->frames++; rc->pic_bits = rbsp_bits;
+  RcFb n = prev;
+  const bool was_paint = f.paint_trigger > 0 && !f.idr && used.paint;
+  if (f.idr || (coded && !was_paint)) { n.static_run = 0; n.remaining = 0; }
+  else if (!coded) {
+    n.static_run = min(prev.static_run + 1, RC_STATIC_PARK);
+    if (f.paint_trigger > 0 && n.static_run == f.paint_trigger) n.remaining = f.paint_burst > 0 ? f.paint_burst : 1;
+  }
+  n.paint = n.remaining > 0;
+  if (n.paint) n.remaining--;
+  if (f.rc_mode == 0) {
+    const long long bits = rbsp_bits + 40LL * f.n_slices;      // + start code and NAL header of every slice
+    const long long T = f.target_bits < 1 ? 1 : f.target_bits;
+    long long full = prev.fullness + bits - T;
+    if (full < -4 * T) full = -4 * T;
+    if (full > 64 * T) full = 64 * T;
+    n.fullness = full;
+    long long budget = T - full / 16;
+    if (budget < T / 2) budget = T / 2;
+    if (budget > 2 * T) budget = 2 * T;
+    const int base = prev.qp < 0 ? rc_initial_qp(T, f.mbw * f.mbh) : prev.qp;
+    int q = base;
+    n.X = f.idr ? 0 : bits * rc_qs[qp_used];
+    if (!f.idr) {
+      const long long lim = budget * rc_qs[qp_used];
+      const long long lo = prev.X > 0 && prev.X < n.X ? prev.X : n.X, hi = prev.X > n.X ? prev.X : n.X;
+      const long long eff = hi > 3 * lo ? lo : (lo + hi) / 2;
+      int qt = base;
+      if (eff * 100 > lim * 104) {
+        const int thr[9] = {104, 119, 133, 150, 168, 189, 238, 300, 378}, stp[9] = {1, 2, 3, 4, 5, 6, 8, 10, 12};
+        int dq = 1;
+#pragma unroll
+        for (int i = 0; i < 9; i++) if (eff * 100 > lim * thr[i]) dq = stp[i];
+        qt = qp_used + dq;
+      } else if (hi * 100 < lim * 88 && full <= 0) {
+        qt = qp_used - ((hi * 2 < lim && full < -2 * T) ? 2 : 1);
+      }
+      q = clip3i(base - 2, base + 4, qt);
+    }
+    n.qp = clip3i(RC_QP_MIN, RC_QP_MAX, q);
+  }
+  rc->fb[f.pic & 1] = n;
 }
 
 // ---- k_slice_scan: one block per slice.  Block-wide scans give every macroblock (a) its mb_skip_run and (b) the bit
@@ -558,7 +579,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
       if (total > cap) { ovf |= 2; total = cap; }
       h->size = (int32_t)total; h->qp = qp; h->is_idr = f.idr; h->n_slices = f.n_slices; h->total_bits = bits;
       h->overflow = ovf;
-      h->next_qp = f.rc->qp;
+      h->next_qp = f.rc->fb[f.pic & 1].qp;         // the controller's decision for the picture two ahead
       h->csc_t0 = f.csc_ts ? f.csc_ts[0] : 0; h->csc_t1 = f.csc_ts ? f.csc_ts[1] : 0;
     }
   }

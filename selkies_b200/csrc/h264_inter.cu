@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
   // full-sample neighbours AND it costs less than the zero vector; quarter-sample refinement then runs as after a search. ----
   bool pred_hit = false, pred_frac = false;
   if (best == 0xffffffffu) {
-    const MbInfo prev = f.mbinfo[mb];                       // still the previous picture's record: rewritten at the end of this kernel
+    const MbInfo prev = f.mbinfo_prev[mb];                  // the previous picture's record (other half of the double buffer)
     const int cdx = (prev.mvx + 2) >> 2, cdy = (prev.mvy + 2) >> 2;
     if (prev.type == MB_P16 && (cdx | cdy) != 0 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
       const uint32_t c0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), c1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);

@@ -216,9 +216,12 @@ class ScreenCapture:
             s.header_mode = N.B2V_HDR_PIXELFLUX       # callers strip / keep the 10-byte header themselves
             s.ring_slots = 4
             s.flags = 0
-            if bool(getattr(settings, "use_paint_over_quality", False)) and not bool(settings.h264_cbr_mode):
+            if bool(getattr(settings, "use_paint_over_quality", False)):
+                # selkies.py:3217, 3226-3229: after paint_over_trigger_frames static pictures, h264_paintover_burst_frames pictures
+                # are coded at h264_paintover_crf (in CBR mode only when that is finer than the rate controller's QP)
                 s.paintover_trigger_frames = int(getattr(settings, "paint_over_trigger_frames", 15) or 0)
                 s.paintover_crf = int(getattr(settings, "h264_paintover_crf", 18))
+                s.paintover_burst_frames = max(1, int(getattr(settings, "h264_paintover_burst_frames", 1) or 1))
             if not bool(getattr(settings, "h264_fullframe", True)):
                 # "x264enc-striped" (selkies.py:3219): independent H.264 stripes, unchanged stripes are not sent
                 sl = max(1, s.slice_rows)

@@ -240,3 +240,29 @@ def test_paintover_bit_exact():
     sy, _ = oracle.csc_nv12(a)
     assert avdec.psnr(dec[k][0], sy) > avdec.psnr(dec[k - 1][0], sy) + 4.0  # the static text got sharper
     assert len(got[k + 1].data) < 150                                        # and is skipped again afterwards
+
+
+def test_paintover_burst_bit_exact():
+    """h264_paintover_burst_frames (selkies.py:3217): `burst` consecutive pictures at the paint-over QP once the trigger is
+    reached; motion cancels what is left of a burst.  Also in CBR mode, where the paint-over QP applies when it is finer."""
+    w, h = 320, 192
+    a, b = natural_frames(w, h)[0], synth.desktop(w, h, 2)
+    frames = [a] * 10 + [b] * 6 + [a] * 9
+    for rc_mode, kw in ((N.B2V_RC_CQP, dict(crf=34)), (N.B2V_RC_CBR, dict(bitrate_kbps=300))):
+        enc = oracle.RefEncoder(w, h, 1)
+        enc.set_paintover(3, 20, burst_frames=3)
+        target = int(300 * 1000 / 30.0)
+        ref = [enc.encode_bgra(f, i == 0, rc_mode=0 if rc_mode == N.B2V_RC_CBR else 1, qp=34, target_bits=target) for i, f in enumerate(frames)]
+        with Session(w, h, rc_mode=rc_mode, fps=30.0, slice_rows=1, paintover_trigger_frames=3, paintover_crf=20, paintover_burst_frames=3, **kw) as s:
+            for f in frames:
+                s.submit(f)
+            s.flush()
+            got = s.take_frames()
+            grec = s.recon()
+        assert_same(got, ref, grec, enc.recon())
+        qps = [g.qp for g in got]
+        if rc_mode == N.B2V_RC_CQP:
+            assert qps[5:8] == [20, 20, 20] and qps[8] == 34 and qps[4] == 34, qps       # trigger after pictures 1..3, two pictures of feedback delay
+            assert 20 in qps[19:] and qps[10:16] == [34] * 6, qps                          # second static period paints again; motion in between does not
+        else:
+            assert min(qps[5:8]) == 20, qps
