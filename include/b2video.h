@@ -79,6 +79,10 @@ typedef struct b2v_settings {
                                delivered by its own callback with y_start/height (10-byte header bytes 4..9,
                                selkies-ws-core.js:3183-3196); a stripe whose macroblocks were all skipped is not
                                delivered.  0 or >= picture rows = full frame */
+  int32_t idr_slice_mbs;    /* IDR pictures only, slice_rows == 1 only: macroblocks per slice INSIDE a row.  The macroblocks of an
+                               intra slice are a serial chain (left-neighbour prediction), so shorter slices shorten the chain the
+                               GPU has to walk (a 4K key frame: 3.3 ms with whole rows).  0 = default (about 540 slices per
+                               picture, none under 30 macroblocks: 60 at 4K, 30 at 1080p), < 0 = whole rows, n = n macroblocks */
   int32_t paintover_burst_frames;   /* CaptureSettings.h264_paintover_burst_frames (selkies.py:3217): how many consecutive
                                        pictures are coded at paintover_crf once the trigger is reached; <= 0 = 1 */
 } b2v_settings;

@@ -107,6 +107,11 @@ class RefEncoder:
         n = self.L.b2v_ref_enc_stripe_table(self.h, t.ctypes.data_as(C.POINTER(C.c_int32)))
         return [tuple(int(v) for v in t[3 * i: 3 * i + 3]) for i in range(n)]
 
+    def set_idr_slice_mbs(self, n: int) -> None:
+        """Slices of IDR pictures: n > 0 macroblocks per slice inside a row, n < 0 whole rows, 0 = the default rule."""
+        self.L.b2v_ref_enc_set_idr_slice_mbs.argtypes = [C.c_void_p, C.c_int]
+        self.L.b2v_ref_enc_set_idr_slice_mbs(self.h, n)
+
     def set_paintover(self, trigger_frames: int, qp: int, burst_frames: int = 1) -> None:
         self.L.b2v_ref_enc_set_paintover(self.h, trigger_frames, qp)
         self.L.b2v_ref_enc_set_paintover_burst.argtypes = [C.c_void_p, C.c_int]

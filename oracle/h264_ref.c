@@ -97,6 +97,10 @@ typedef struct {
 #define MAX_STRIPES 512
 typedef struct {
   int width, height, cw, ch, mbw, mbh, slice_rows, n_slices;
+  /* IDR pictures may be cut finer than rows: slices of `seg_cols` macroblocks inside a row (only with slice_rows == 1).  The
+   * macroblocks of an intra slice are a serial chain (left-neighbour prediction), so shorter slices = a shorter chain on the
+   * GPU.  pic_seg is the value in force for the picture being coded (0 = whole rows). */
+  int seg_cols, pic_seg;
   uint8_t* recon[2];      /* NV12, coded size; recon[cur] is being written, recon[cur^1] is the reference */
   int cur;
   mb_t* mbs;
@@ -265,7 +269,17 @@ static uint8_t* plane_y(enc_t* e, int idx) { return e->recon[idx]; }
 static uint8_t* plane_uv(enc_t* e, int idx) { return e->recon[idx] + (size_t)e->cw * e->ch; }
 
 static int slice_first_row(const enc_t* e, int mby) { return (mby / e->slice_rows) * e->slice_rows; }
-static int avail_top(const enc_t* e, int mby) { return mby > slice_first_row(e, mby); }
+static int avail_top(const enc_t* e, int mby) { return e->pic_seg ? 0 : mby > slice_first_row(e, mby); }
+static int avail_left(const enc_t* e, int mbx) { return e->pic_seg ? (mbx % e->pic_seg) != 0 : mbx > 0; }
+static int pic_segs(const enc_t* e) { return e->pic_seg ? (e->mbw + e->pic_seg - 1) / e->pic_seg : 1; }
+static int pic_n_slices(const enc_t* e) { return e->pic_seg ? e->mbh * pic_segs(e) : e->n_slices; }
+/* default IDR slicing: about 540 slices per picture, none shorter than 30 macroblocks */
+static int auto_seg_cols(int mbw, int mbh) {
+  int segs = 540 / mbh, cap = mbw / 30;
+  if (segs > cap) segs = cap;
+  if (segs <= 1) return 0;
+  return (mbw + segs - 1) / segs;
+}
 static void make_pcm_if_too_big(enc_t* e, mb_t* m, const uint8_t* cur_nv12, int mbx, int mby);   /* defined after the CAVLC coder */
 static void cavlc_block(bitw_t* b, const int16_t* lv, int start, int maxc, int nC);
 
@@ -422,7 +436,7 @@ static int i4_pred_mode(const enc_t* e, int mbx, int mby, int bx, int by) {
   const mb_t* m = &e->mbs[mby * e->mbw + mbx];
   int ma, mb_;
   if (bx > 0) ma = m->i4_modes[by * 4 + bx - 1];
-  else { if (mbx == 0) return 2; const mb_t* n = m - 1; ma = n->type == 3 ? n->i4_modes[by * 4 + 3] : 2; }
+  else { if (!avail_left(e, mbx)) return 2; const mb_t* n = m - 1; ma = n->type == 3 ? n->i4_modes[by * 4 + 3] : 2; }
   if (by > 0) mb_ = m->i4_modes[(by - 1) * 4 + bx];
   else { if (!avail_top(e, mby)) return 2; const mb_t* n = m - e->mbw; mb_ = n->type == 3 ? n->i4_modes[12 + bx] : 2; }
   return ma < mb_ ? ma : mb_;
@@ -435,7 +449,7 @@ static const uint8_t i4_tr_inside[16] = { 2,2,2,3, 1,0,1,0, 1,1,1,0, 1,0,1,0 }; 
 static int intra4x4_pass(enc_t* e, mb_t* m, const uint8_t cy[256], int mbx, int mby, int qp) {
   uint8_t* ry = plane_y(e, e->cur);
   const int x0 = mbx * 16, y0 = mby * 16, lambda = me_lambda[qp];
-  const int mb_left = mbx > 0, mb_top = avail_top(e, mby), mb_tr = mb_top && mbx + 1 < e->mbw;
+  const int mb_left = avail_left(e, mbx), mb_top = avail_top(e, mby), mb_tr = mb_top && mbx + 1 < e->mbw;
   int cost = 0;
   for (int blk = 0; blk < 16; blk++) {
     const int bx = blk_x[blk], by = blk_y[blk], px = x0 + bx * 4, py = y0 + by * 4;
@@ -478,7 +492,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   m->type = 0;
   uint8_t cy[256], cc[2][64];
   load_cur(cur_nv12, e->cw, e->ch, mbx, mby, cy, cc);
-  int has_left = mbx > 0, has_top = avail_top(e, mby);
+  int has_left = avail_left(e, mbx), has_top = avail_top(e, mby);
   uint8_t* ry = plane_y(e, e->cur); uint8_t* ruv = plane_uv(e, e->cur);
   uint8_t top[16] = {0}, left[16] = {0}; int tl = 0;
   uint8_t ctop[2][8] = {{0}}, cleft[2][8] = {{0}}; int ctl[2] = {0, 0};
@@ -849,7 +863,7 @@ static void cavlc_block(bitw_t* b, const int16_t* lv, int start, int maxc, int n
 static int mb_avail(const enc_t* e, int mbx, int mby, int nx, int ny) {
   if (nx < 0 || nx >= e->mbw || ny < 0) return 0;
   if (ny != mby && !avail_top(e, mby)) return 0;
-  (void)mbx;
+  if (nx != mbx && !avail_left(e, mbx)) return 0;
   return 1;
 }
 static int nnz_luma_at(const enc_t* e, const uint8_t* skip, int mbx, int mby, int bx, int by, int* ok) {
@@ -881,7 +895,7 @@ static int calc_nc(int na, int oka, int nb, int okb) { return oka && okb ? (na +
 static void mv_neighbours(const enc_t* e, int mbx, int mby, int av[3], int ref0[3], int mv[3][2]) {
   int top = avail_top(e, mby);
   int nx[3] = { mbx - 1, mbx, mbx + 1 }, ny[3] = { mby, mby - 1, mby - 1 };
-  av[0] = mbx > 0; av[1] = top; av[2] = top && mbx + 1 < e->mbw;
+  av[0] = avail_left(e, mbx); av[1] = top; av[2] = top && mbx + 1 < e->mbw;
   if (!av[2]) { nx[2] = mbx - 1; av[2] = top && mbx > 0; }    /* C unavailable -> D */
   for (int i = 0; i < 3; i++) {
     mv[i][0] = mv[i][1] = 0; ref0[i] = 0;
@@ -902,7 +916,7 @@ static void mv_pred16(const enc_t* e, int mbx, int mby, int out[2]) {
   out[1] = median3(mv[0][1], mv[1][1], mv[2][1]);
 }
 static void mv_pred_skip(const enc_t* e, int mbx, int mby, int out[2]) {
-  int okA = mbx > 0, okB = avail_top(e, mby);
+  int okA = avail_left(e, mbx), okB = avail_top(e, mby);
   out[0] = out[1] = 0;
   if (!okA || !okB) return;
   const mb_t* a = &e->mbs[mby * e->mbw + mbx - 1]; const mb_t* b = &e->mbs[(mby - 1) * e->mbw + mbx];
@@ -981,13 +995,15 @@ static void write_slice_header(const enc_t* e, bitw_t* b, int first_mb, int idr,
 /* entropy-code one slice (7.3.4, 7.3.5) into a NAL appended at out; returns bytes written */
 static size_t code_slice(enc_t* e, int s, int idr, int qp, uint8_t* skip, uint8_t* out, int64_t* bits) {
   bitw_t b; bw_init(&b);
-  int row0 = s * e->slice_rows, row1 = row0 + e->slice_rows; if (row1 > e->mbh) row1 = e->mbh;
+  int row0 = s * e->slice_rows, row1 = row0 + e->slice_rows, x0 = 0, x1 = e->mbw;
+  if (e->pic_seg) { const int segs = pic_segs(e); row0 = s / segs; row1 = row0 + 1; x0 = (s % segs) * e->pic_seg; x1 = x0 + e->pic_seg; if (x1 > e->mbw) x1 = e->mbw; }
+  if (row1 > e->mbh) row1 = e->mbh;
   int br0, br1; band_rows(e, row0, &br0, &br1);
-  const int first_nal_of_au = row0 == br0 && !idr;     /* 4-byte start code opens each band's access unit */
-  write_slice_header(e, &b, (row0 - br0) * e->mbw, idr, qp, idr ? 0 : e->stripe_rows ? e->stripe_fn[row0 / e->stripe_rows] : e->frame_num);
+  const int first_nal_of_au = row0 == br0 && x0 == 0 && !idr;     /* 4-byte start code opens each band's access unit */
+  write_slice_header(e, &b, (row0 - br0) * e->mbw + x0, idr, qp, idr ? 0 : e->stripe_rows ? e->stripe_fn[row0 / e->stripe_rows] : e->frame_num);
   int skip_run = 0;
   for (int mby = row0; mby < row1; mby++)
-    for (int mbx = 0; mbx < e->mbw; mbx++) {
+    for (int mbx = x0; mbx < x1; mbx++) {
       const mb_t* m = &e->mbs[mby * e->mbw + mbx];
       if (!idr) {
         int sp[2];
@@ -1132,6 +1148,7 @@ void* b2v_ref_enc_create(int width, int height, int slice_rows) {
   e->recon[0] = (uint8_t*)calloc(fb, 1); e->recon[1] = (uint8_t*)calloc(fb, 1);
   e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
   e->fb[0].qp = e->fb[1].qp = -1; e->paint_burst = 1;
+  e->seg_cols = e->slice_rows == 1 ? auto_seg_cols(e->mbw, e->mbh) : 0;
   e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL;
   write_param_sets(e);
   return e;
@@ -1146,6 +1163,11 @@ int b2v_ref_enc_coded_h(void* h) { return ((enc_t*)h)->ch; }
 const uint8_t* b2v_ref_enc_recon(void* h) { enc_t* e = (enc_t*)h; return e->recon[e->cur]; }
 int b2v_ref_enc_last_qp(void* h) { return ((enc_t*)h)->last_qp; }
 void b2v_ref_enc_set_paintover(void* h, int trigger_frames, int qp) { enc_t* e = (enc_t*)h; e->paint_trigger = trigger_frames; e->paint_qp = qp; }
+/* slices of IDR pictures: n > 0 macroblocks per slice inside a row, n < 0 whole rows, 0 = the default rule; needs slice_rows == 1 */
+void b2v_ref_enc_set_idr_slice_mbs(void* h, int n) {
+  enc_t* e = (enc_t*)h;
+  e->seg_cols = e->slice_rows != 1 || n < 0 ? 0 : n == 0 ? auto_seg_cols(e->mbw, e->mbh) : n >= e->mbw ? 0 : n;
+}
 void b2v_ref_enc_set_paintover_burst(void* h, int burst_frames) { ((enc_t*)h)->paint_burst = burst_frames > 0 ? burst_frames : 1; }
 /* striped mode: stripe_rows macroblock rows per band (a multiple of slice_rows); 0 = full frame.  Returns the band count or -1. */
 int b2v_ref_enc_set_stripes(void* h, int stripe_rows) {
@@ -1181,15 +1203,19 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   const struct rcfb used = e->fb[k];                         /* the controller state after picture pic-2 */
   const int qp = rc_frame_qp(e, &used, idr, rc_mode, qp_fixed, target_bits);
   e->cur ^= 1;
+  e->pic_seg = idr ? e->seg_cols : 0;
+  const int nsl = pic_n_slices(e);
   if (idr) { e->frame_num = 0; }
   /* phase A: analysis + reconstruction.  Intra: macroblocks of a slice are sequential (left/top
    * dependencies), slices are independent.  Inter: every macroblock is independent. */
   if (idr) {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int s = 0; s < e->n_slices; s++) {
-      int row1 = (s + 1) * e->slice_rows; if (row1 > e->mbh) row1 = e->mbh;
-      for (int mby = s * e->slice_rows; mby < row1; mby++)
-        for (int mbx = 0; mbx < e->mbw; mbx++) encode_intra_mb(e, cur_nv12, mbx, mby, qp);
+    for (int s = 0; s < nsl; s++) {
+      int row0 = s * e->slice_rows, row1 = (s + 1) * e->slice_rows, x0 = 0, x1 = e->mbw;
+      if (e->pic_seg) { const int segs = pic_segs(e); row0 = s / segs; row1 = row0 + 1; x0 = (s % segs) * e->pic_seg; x1 = x0 + e->pic_seg; if (x1 > e->mbw) x1 = e->mbw; }
+      if (row1 > e->mbh) row1 = e->mbh;
+      for (int mby = row0; mby < row1; mby++)
+        for (int mbx = x0; mbx < x1; mbx++) encode_intra_mb(e, cur_nv12, mbx, mby, qp);
     }
   } else {
 #pragma omp parallel for schedule(dynamic, 1)
@@ -1199,15 +1225,16 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
   /* phase B: entropy coding per slice, then concatenation */
   uint8_t* skip = (uint8_t*)calloc(mbs, 1);
   size_t per = (size_t)e->slice_rows * e->mbw * 1024 + 256;
-  uint8_t* tmp = (uint8_t*)malloc(per * e->n_slices);
-  size_t* lens = (size_t*)calloc(e->n_slices, sizeof(size_t));
-  int64_t* sbits = (int64_t*)calloc(e->n_slices, sizeof(int64_t));
+  if (e->pic_seg) per = (size_t)e->pic_seg * 1024 + 256;
+  uint8_t* tmp = (uint8_t*)malloc(per * nsl);
+  size_t* lens = (size_t*)calloc(nsl, sizeof(size_t));
+  int64_t* sbits = (int64_t*)calloc(nsl, sizeof(int64_t));
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int s = 0; s < e->n_slices; s++) lens[s] = code_slice(e, s, idr, qp, skip, tmp + per * s, &sbits[s]);
+  for (int s = 0; s < nsl; s++) lens[s] = code_slice(e, s, idr, qp, skip, tmp + per * s, &sbits[s]);
   size_t o = 0; int64_t bits = 0;
   if (!e->stripe_rows) {
     if (idr) { memcpy(out + o, e->sps, e->sps_len); o += e->sps_len; memcpy(out + o, e->pps, e->pps_len); o += e->pps_len; }
-    for (int s = 0; s < e->n_slices; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
+    for (int s = 0; s < nsl; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
   } else {
     /* bands back to back, each a complete access unit of its own stream; a P band whose macroblocks were all skipped
      * is flagged not-coded (the caller drops it) and its frame_num does not advance */
@@ -1216,7 +1243,8 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
       const int last = t == e->n_stripes - 1;
       const size_t o0 = o;
       if (idr) { memcpy(out + o, e->sps_band[last], e->sps_band_len[last]); o += e->sps_band_len[last]; memcpy(out + o, e->pps, e->pps_len); o += e->pps_len; }
-      for (int s = r0 / e->slice_rows; s < (r1 + e->slice_rows - 1) / e->slice_rows; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
+      const int s0 = e->pic_seg ? r0 * pic_segs(e) : r0 / e->slice_rows, s1 = e->pic_seg ? r1 * pic_segs(e) : (r1 + e->slice_rows - 1) / e->slice_rows;
+      for (int s = s0; s < s1; s++) { memcpy(out + o, tmp + per * s, lens[s]); o += lens[s]; bits += sbits[s]; }
       int coded = idr;
       for (int i = r0 * e->mbw; i < r1 * e->mbw && !coded; i++) coded |= !skip[i];
       e->stripe_tab[t][0] = (int32_t)o0; e->stripe_tab[t][1] = (int32_t)(o - o0); e->stripe_tab[t][2] = coded;
@@ -1230,7 +1258,7 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
     const struct rcfb prev = e->pic > 0 ? e->fb[k ^ 1] : init;
     /* RBSP bits of the slices: known before the byte stream is assembled */
     /* + 40 bits per slice NAL (start code, NAL header): what the wire carries beyond the RBSP, to a good approximation */
-    rc_step(e, &e->fb[k], &prev, &used, bits + 40LL * e->n_slices, qp, idr, coded, rc_mode, target_bits); }
+    rc_step(e, &e->fb[k], &prev, &used, bits + 40LL * nsl, qp, idr, coded, rc_mode, target_bits); }
   e->last_qp = qp; e->last_bits = (int64_t)o * 8; e->pic++;
   if (idr) e->idr_count++;
   e->frame_num = (e->frame_num + 1) & 255;

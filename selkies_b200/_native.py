@@ -25,7 +25,7 @@ class B2VSettings(C.Structure):
         ("fps", C.c_double), ("device", C.c_int32), ("rc_mode", C.c_int32),
         ("bitrate_kbps", C.c_int32), ("crf", C.c_int32), ("gop", C.c_int32),
         ("slice_rows", C.c_int32), ("header_mode", C.c_int32), ("ring_slots", C.c_int32),
-        ("flags", C.c_int32), ("paintover_trigger_frames", C.c_int32), ("paintover_crf", C.c_int32), ("stripe_rows", C.c_int32), ("paintover_burst_frames", C.c_int32),
+        ("flags", C.c_int32), ("paintover_trigger_frames", C.c_int32), ("paintover_crf", C.c_int32), ("stripe_rows", C.c_int32), ("idr_slice_mbs", C.c_int32), ("paintover_burst_frames", C.c_int32),
     ]
 
 

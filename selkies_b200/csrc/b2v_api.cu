@@ -169,6 +169,7 @@ int alloc_geometry(Session* s) {
     ec.slice_rows = s->cfg.slice_rows > 0 ? s->cfg.slice_rows : 1;
     ec.sm_count = s->sm_count;
     ec.stripe_rows = s->cfg.stripe_rows > 0 ? s->cfg.stripe_rows : 0;
+    ec.idr_slice_mbs = s->cfg.idr_slice_mbs;
     int rc = encoder_create(&ec, &s->enc);
     if (rc) return fail(rc, "encoder_create failed: %s", encoder_last_error());
     s->au_cap = encoder_au_capacity(s->enc);

@@ -52,7 +52,9 @@ __device__ const int32_t rc_qs[52] = {
   14596, 16384, 18390, 20643, 23170};
 
 struct FrameCtx {          // everything a kernel needs about the picture being coded
-  int cw, ch, mbw, mbh, slice_rows, n_slices;
+  int cw, ch, mbw, mbh, slice_rows, n_slices;   // n_slices: of THIS picture
+  int seg_cols;            // > 0 (IDR pictures with slice_rows == 1 only): slices of seg_cols macroblocks inside a row — the macroblocks
+                           // of an intra slice are a serial chain, so shorter slices shorten the chain; 0 = whole rows
   int idr, rc_mode, qp_fixed;
   int paint_trigger, paint_qp, paint_burst;   // paint-over: `paint_burst` refinement pictures after `paint_trigger` all-skipped pictures (0 = off)
   int pic;                 // picture counter of this encoder (parity selects the feedback record and the double-buffered side data)
@@ -110,7 +112,21 @@ __device__ __forceinline__ int frame_qp(const FrameCtx& f) {
   if (paint && f.paint_qp < q) q = clip3i(0, 51, f.paint_qp);
   return q;
 }
-__device__ __forceinline__ bool top_in_slice(const FrameCtx& f, int mby) { return (mby % f.slice_rows) != 0; }
+// slice geometry (mirrors oracle/h264_ref.c avail_top / avail_left / code_slice)
+__device__ __forceinline__ bool top_in_slice(const FrameCtx& f, int mby) { return f.seg_cols ? false : (mby % f.slice_rows) != 0; }
+__device__ __forceinline__ bool left_in_slice(const FrameCtx& f, int mbx) { return f.seg_cols ? (mbx % f.seg_cols) != 0 : mbx > 0; }
+__device__ __forceinline__ int segs_per_row(const FrameCtx& f) { return f.seg_cols ? (f.mbw + f.seg_cols - 1) / f.seg_cols : 1; }
+__device__ __forceinline__ int slice_of(const FrameCtx& f, int mbx, int mby) { return f.seg_cols ? mby * segs_per_row(f) + mbx / f.seg_cols : mby / f.slice_rows; }
+struct SliceGeo { int row0, row1, x0, x1, mb0, n_mb; };      // macroblock rows [row0,row1) x columns [x0,x1); mb0 = first macroblock
+__device__ __forceinline__ SliceGeo slice_geo(const FrameCtx& f, int s) {
+  SliceGeo g;
+  if (f.seg_cols) {
+    const int segs = segs_per_row(f);
+    g.row0 = s / segs; g.row1 = g.row0 + 1; g.x0 = (s - g.row0 * segs) * f.seg_cols; g.x1 = min(f.mbw, g.x0 + f.seg_cols);
+  } else { g.row0 = s * f.slice_rows; g.row1 = min(f.mbh, g.row0 + f.slice_rows); g.x0 = 0; g.x1 = f.mbw; }
+  g.mb0 = g.row0 * f.mbw + g.x0; g.n_mb = (g.row1 - g.row0) * (g.x1 - g.x0);
+  return g;
+}
 
 __device__ __forceinline__ int pos_class(int r) { int x = r & 3, y = r >> 2; return ((x | y) & 1) == 0 ? 0 : ((x & y) & 1) ? 1 : 2; }
 

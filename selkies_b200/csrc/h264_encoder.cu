@@ -20,6 +20,7 @@ const char* encoder_last_error() { return g_enc_err; }
 struct Encoder {
   EncoderConfig cfg{};
   int mbw = 0, mbh = 0, n_slices = 0;
+  int seg_cols = 0, n_seg_slices = 0, seg_slice_words = 0;   // IDR pictures: sub-row slices (0 = whole rows)
   uint8_t* recon[2] = {nullptr, nullptr};
   int cur = 0;
   // side data the analysis kernels write and the entropy kernels read: double-buffered by picture parity, so the entropy coding
@@ -154,11 +155,22 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMalloc((void**)&e->mb_off, mbs * sizeof(long long)));
   ECK(cudaMalloc((void**)&e->mb_run, mbs * sizeof(int)));
   e->slice_words = cfg->slice_rows * e->mbw * MB_WORDS + 64;
-  ECK(cudaMalloc((void**)&e->slice_buf, (size_t)e->n_slices * e->slice_words * sizeof(uint32_t)));
-  ECK(cudaMemset(e->slice_buf, 0, (size_t)e->n_slices * e->slice_words * sizeof(uint32_t)));
-  ECK(cudaMalloc((void**)&e->slice_size, e->n_slices * sizeof(uint32_t)));
-  ECK(cudaMalloc((void**)&e->slice_rbsp, e->n_slices * sizeof(uint32_t)));
-  ECK(cudaMalloc((void**)&e->slice_bits, e->n_slices * sizeof(long long)));
+  // IDR pictures: slices shorter than a row (same rule as oracle/h264_ref.c auto_seg_cols: about 540 slices, none under 30 macroblocks)
+  if (cfg->slice_rows == 1 && cfg->idr_slice_mbs >= 0) {
+    int cols = cfg->idr_slice_mbs;
+    if (cols == 0) { int segs = 540 / e->mbh; const int cap = e->mbw / 30; if (segs > cap) segs = cap; cols = segs <= 1 ? 0 : (e->mbw + segs - 1) / segs; }
+    if (cols >= e->mbw) cols = 0;
+    e->seg_cols = cols;
+  }
+  if (e->seg_cols) { e->n_seg_slices = e->mbh * ((e->mbw + e->seg_cols - 1) / e->seg_cols); e->seg_slice_words = e->seg_cols * MB_WORDS + 64; }
+  const size_t nsl_max = (size_t)(e->n_seg_slices > e->n_slices ? e->n_seg_slices : e->n_slices);
+  size_t sb_words = (size_t)e->n_slices * e->slice_words;
+  if ((size_t)e->n_seg_slices * e->seg_slice_words > sb_words) sb_words = (size_t)e->n_seg_slices * e->seg_slice_words;
+  ECK(cudaMalloc((void**)&e->slice_buf, sb_words * sizeof(uint32_t)));
+  ECK(cudaMemset(e->slice_buf, 0, sb_words * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->slice_size, nsl_max * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->slice_rbsp, nsl_max * sizeof(uint32_t)));
+  ECK(cudaMalloc((void**)&e->slice_bits, nsl_max * sizeof(long long)));
   ECK(cudaMalloc((void**)&e->progress, e->mbh * sizeof(int)));
   ECK(cudaMalloc((void**)&e->overflow, sizeof(int)));
   ECK(cudaMemset(e->overflow, 0, sizeof(int)));
@@ -189,7 +201,7 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
     ECK(cudaEventCreateWithFlags(&e->ev_analysed[b], cudaEventDisableTiming));
     ECK(cudaEventCreateWithFlags(&e->ev_packed[b], cudaEventDisableTiming));
   }
-  e->au_cap = (size_t)e->au_data_off + (size_t)e->n_bands * (e->param_len + e->param_len_last) + (size_t)e->n_slices * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
+  e->au_cap = (size_t)e->au_data_off + (size_t)e->n_bands * (e->param_len + e->param_len_last) + nsl_max * 16 + mbs * (MB_WORDS * 4 + 8) + 1024;
   *out = e;
   return 0;
 }
@@ -219,13 +231,14 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   if (idr) e->frame_num = 0;
   FrameCtx f{};
   f.cw = e->cfg.coded_w; f.ch = e->cfg.coded_h; f.mbw = e->mbw; f.mbh = e->mbh;
-  f.slice_rows = e->cfg.slice_rows; f.n_slices = e->n_slices;
+  const bool seg = idr && e->seg_cols > 0;
+  f.slice_rows = e->cfg.slice_rows; f.n_slices = seg ? e->n_seg_slices : e->n_slices; f.seg_cols = seg ? e->seg_cols : 0;
   f.idr = idr; f.rc_mode = p->rc_mode; f.qp_fixed = p->qp_fixed; f.target_bits = p->target_bits;
   f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count; f.pic = (int)(e->pic & 0x7fffffff);
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
   f.mbinfo = e->mbinfo[par]; f.mbinfo_prev = e->mbinfo[par ^ 1]; f.i4modes = e->i4modes[par]; f.coef = e->coef[par]; f.nnz = e->nnz[par];
   f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
-  f.slice_buf = e->slice_buf; f.slice_words = e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
+  f.slice_buf = e->slice_buf; f.slice_words = seg ? e->seg_slice_words : e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
   f.slice_bits = e->slice_bits; f.paint_trigger = p->paint_trigger; f.paint_qp = p->paint_qp; f.paint_burst = p->paint_burst; f.progress = e->progress; f.rc = e->rc;
   f.band_rows = e->band_rows; f.n_bands = e->n_bands; f.striped = e->striped; f.param_len_last = e->param_len_last;
   f.band_fn = e->band_fn; f.band_coded = e->band_coded; f.au_data_off = e->au_data_off;

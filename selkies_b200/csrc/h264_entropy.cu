@@ -29,7 +29,7 @@ struct MvCtx { bool avA, avB, avC, rA, rB, rC; int ax, ay, bx, by, cx, cy; };
 __device__ __forceinline__ MvCtx mv_ctx(const FrameCtx& f, int mbx, int mby) {
   MvCtx m;
   const bool top = top_in_slice(f, mby);
-  m.avA = mbx > 0; m.avB = top; m.avC = top && mbx + 1 < f.mbw;
+  m.avA = left_in_slice(f, mbx); m.avB = top; m.avC = top && mbx + 1 < f.mbw;
   int cxi = mbx + 1;
   if (!m.avC) { cxi = mbx - 1; m.avC = top && mbx > 0; }      // C unavailable -> D
   m.ax = m.ay = m.bx = m.by = m.cx = m.cy = 0;
@@ -58,7 +58,7 @@ template <class S>
 __device__ __forceinline__ void mb_header_i4(S& h, const FrameCtx& f, const MbInfo& mi, int mb, int mbx, int mby) {
   put_ue(h, f.idr ? 0u : 5u);
   const uint8_t* own = f.i4modes + (size_t)mb * 16;
-  const bool availA = mbx > 0, availB = top_in_slice(f, mby);
+  const bool availA = left_in_slice(f, mbx), availB = top_in_slice(f, mby);
   const bool a_i4 = availA && f.mbinfo[mb - 1].type == MB_I4, b_i4 = availB && f.mbinfo[mb - f.mbw].type == MB_I4;
   for (int blk = 0; blk < 16; blk++) {
     const int bx = blk_x[blk], by = blk_y[blk], mode = own[by * 4 + bx];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
   // ---- which block does this lane code, and with which nC ---------------------------------------------
   // lane 0: Intra16x16 DC | 1..16: luma blkIdx lane-1 | 17,18: chroma DC | 19..26: chroma AC
   const uint8_t* nz_own = f.nnz + (size_t)mb * 32;
-  const bool availA = mbx > 0, availB = top_in_slice(f, mby);
+  const bool availA = left_in_slice(f, mbx), availB = top_in_slice(f, mby);
   const uint8_t* nz_a = f.nnz + (size_t)(mb - 1) * 32;
   const uint8_t* nz_b = f.nnz + (size_t)(mb - f.mbw) * 32;
   bool coded = false; int start = 0, maxc = 16, nC = 0, cblk = lane;
@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
   __shared__ int s_run[SLICE_THREADS];
   __shared__ long long s_off[SLICE_THREADS];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = s * f.slice_rows, row1 = min(f.mbh, row0 + f.slice_rows);
-  const int mb0 = row0 * f.mbw, n_mb = (row1 - row0) * f.mbw;
+  const SliceGeo geo = slice_geo(f, s);
+  const int row0 = geo.row0, mb0 = geo.mb0, n_mb = geo.n_mb;
   const int qp = frame_qp(f);
   uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
   if (tid == 0) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(COPY_THREADS) k_slice_copy(FrameCtx f) {
   if (v >> 31) return;                                       // P_Skip: folded into a later mb_skip_run
   const bool pcm = ((v >> 30) & 1u) != 0;
   const uint32_t nbits = v & 0x3fffffffu;
-  const int mby = mb / f.mbw, mbx = mb - mby * f.mbw, s = mby / f.slice_rows;
+  const int mby = mb / f.mbw, mbx = mb - mby * f.mbw, s = slice_of(f, mbx, mby);
   uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
   long long pos = f.mb_off[mb];
   if (!f.idr) {
@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_ep(FrameCtx f) {
   if (tid == 0) {
     int t = 0;
     for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_red[w];
-    const int start_len = ((s * f.slice_rows) % f.band_rows == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of (each band's) access unit
+    const SliceGeo geo = slice_geo(f, s);
+    const int start_len = (geo.row0 % f.band_rows == 0 && geo.x0 == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of (each band's) access unit
     f.slice_size[s] = (uint32_t)(start_len + 1 + rbsp_bytes + t);
   }
 }
@@ -487,8 +488,9 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
   __shared__ long long s_part[PACK_THREADS / 32];
   if (lane == 0) s_part[warp] = part;
   __syncthreads();
-  const int row0 = s * f.slice_rows, band = row0 / f.band_rows;
-  const bool band_first = row0 == band * f.band_rows;                     // this slice opens its band's access unit
+  const SliceGeo geo = slice_geo(f, s);
+  const int row0 = geo.row0, band = row0 / f.band_rows;
+  const bool band_first = row0 == band * f.band_rows && geo.x0 == 0;      // this slice opens its band's access unit
   const int plen = (f.striped && band == f.n_bands - 1) ? f.param_len_last : f.param_len;
   if (tid == 0) {
     long long t = f.idr ? (long long)band * f.param_len + plen : 0;       // parameter sets of bands 0..band precede this NAL
@@ -560,7 +562,8 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_au(FrameCtx f, long long 
     }
     if (f.striped && tid == 0) {      // band table entry; the band's frame_num advances only if it is delivered
       long long sz = f.idr ? plen : 0;
-      const int s1 = min(f.n_slices, (min(f.mbh, (band + 1) * f.band_rows) + f.slice_rows - 1) / f.slice_rows);
+      const int band_row1 = min(f.mbh, (band + 1) * f.band_rows);
+      const int s1 = min(f.n_slices, f.seg_cols ? band_row1 * segs_per_row(f) : (band_row1 + f.slice_rows - 1) / f.slice_rows);
       for (int j = s; j < s1; j++) sz += f.slice_size[j];
       const int coded = f.idr ? 1 : f.band_coded[band];
       const int fn = f.idr ? 0 : f.band_fn[band];

@@ -87,7 +87,7 @@ __host__ __device__ constexpr int se_bits_c(int v) {
   return 2 * len + 1;
 }
 
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_inter_mb(FrameCtx f) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f) {
   __shared__ __align__(16) InterSm sm_all[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mb = blockIdx.x * WARPS_PER_BLOCK + warp;

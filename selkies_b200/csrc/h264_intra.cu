@@ -129,11 +129,13 @@ __global__ void __launch_bounds__(96) k_intra_rows(FrameCtx f) {
   __shared__ __align__(16) IntraNb nb;
   __shared__ __align__(16) I4State i4;
   __shared__ I4Result r4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, mby = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const SliceGeo geo = slice_geo(f, f.seg_cols ? (int)blockIdx.x : (int)blockIdx.x / f.slice_rows);   // sub-row slices: one block per slice
+  const int mby = f.seg_cols ? geo.row0 : (int)blockIdx.x, mbx0 = f.seg_cols ? geo.x0 : 0, mbx1 = f.seg_cols ? geo.x1 : f.mbw;
   const int qp = frame_qp(f);
   const int lambda = me_lambda[qp];
   const bool has_top = top_in_slice(f, mby);
-  const bool signal_progress = f.slice_rows > 1 && mby + 1 < f.mbh && top_in_slice(f, mby + 1);
+  const bool signal_progress = !f.seg_cols && f.slice_rows > 1 && mby + 1 < f.mbh && top_in_slice(f, mby + 1);
   const size_t ysz = (size_t)f.cw * f.ch;
   const uint8_t* cur_y = f.cur; const uint8_t* cur_uv = f.cur + ysz;
   uint8_t* rec_y = f.recon; uint8_t* rec_uv = f.recon + ysz;
@@ -152,9 +154,9 @@ __global__ void __launch_bounds__(96) k_intra_rows(FrameCtx f) {
   const uint32_t cm = *reinterpret_cast<const uint32_t*>(&i4.code[lm][ly * 4]);   // V-indices of this lane's four predicted samples
   const uint32_t ch = *reinterpret_cast<const uint32_t*>(&i4.code[8][ly * 4]);    // ... for horizontal-up
 
-  for (int mbx = 0; mbx < f.mbw; mbx++) {
+  for (int mbx = mbx0; mbx < mbx1; mbx++) {
     const int mb = mby * f.mbw + mbx;
-    const bool has_left = mbx > 0;
+    const bool has_left = mbx > mbx0;
     const bool has_tr = has_top && mbx + 1 < f.mbw;
     if (has_top) {       // wavefront: the row above must have finished macroblock mbx+1 (above-right samples)
       if (threadIdx.x == 0) { const int need = min(mbx + 2, f.mbw); while (*((volatile int*)&f.progress[mby - 1]) < need) { } __threadfence(); }
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(96) k_intra_rows(FrameCtx f) {
 
 int launch_intra(const FrameCtx& f, cudaStream_t st) {
   cudaMemsetAsync(f.progress, 0, sizeof(int) * f.mbh, st);
-  k_intra_rows<<<f.mbh, 96, 0, st>>>(f);
+  k_intra_rows<<<f.seg_cols ? f.n_slices : f.mbh, 96, 0, st>>>(f);
   return 1;
 }
 

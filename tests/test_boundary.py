@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from selkies_b200 import _native as N
-    assert ctypes.sizeof(N.B2VSettings) == 4 * 4 + 8 + 9 * 4 + 4 * 4 + 4    # padded to 8
+    assert ctypes.sizeof(N.B2VSettings) == 4 * 4 + 8 + 14 * 4               # 80 bytes, a multiple of 8
     assert ctypes.sizeof(N.B2VFrame) == 8 + 4 * 4 + 8 + 8 + 2 * 4 and N.B2VFrame.y_start.offset == 40
     assert N.B2VSettings.fps.offset == 16 and N.B2VSettings.device.offset == 24
     assert ctypes.sizeof(N.B2VStats) == 7 * 8 + 7 * 8 + 6 * 8 + 2 * 8 + 8 * 8 and N.B2VStats.ns_wait_event.offset == 22 * 8

@@ -246,8 +246,8 @@ def test_paintover_burst_bit_exact():
     """h264_paintover_burst_frames (selkies.py:3217): `burst` consecutive pictures at the paint-over QP once the trigger is
     reached; motion cancels what is left of a burst.  Also in CBR mode, where the paint-over QP applies when it is finer."""
     w, h = 320, 192
-    a, b = natural_frames(w, h)[0], synth.desktop(w, h, 2)
-    frames = [a] * 10 + [b] * 6 + [a] * 9
+    a = natural_frames(w, h)[0]
+    frames = [a] * 10 + [synth.desktop(w, h, t) for t in range(6)] + [a] * 22      # static, six pictures of motion, static again
     for rc_mode, kw in ((N.B2V_RC_CQP, dict(crf=34)), (N.B2V_RC_CBR, dict(bitrate_kbps=300))):
         enc = oracle.RefEncoder(w, h, 1)
         enc.set_paintover(3, 20, burst_frames=3)
@@ -263,6 +263,57 @@ def test_paintover_burst_bit_exact():
         qps = [g.qp for g in got]
         if rc_mode == N.B2V_RC_CQP:
             assert qps[5:8] == [20, 20, 20] and qps[8] == 34 and qps[4] == 34, qps       # trigger after pictures 1..3, two pictures of feedback delay
-            assert 20 in qps[19:] and qps[10:16] == [34] * 6, qps                          # second static period paints again; motion in between does not
+            # motion never paints; the second static period paints again once its last small refinements have died out
+            assert qps[8:26] == [34] * 18 and qps[26:].count(20) == 3, qps
         else:
             assert min(qps[5:8]) == 20, qps
+
+
+@pytest.mark.parametrize("w,h,mbs", [(320, 192, 7), (320, 192, 10), (130, 70, 3), (640, 368, 40), (320, 192, -1)])
+def test_idr_subrow_slices_bit_exact(w, h, mbs):
+    """IDR pictures cut into slices shorter than a macroblock row (b2v_settings.idr_slice_mbs): left/top availability, nC
+    contexts, Intra4x4 mode prediction and first_mb_in_slice all follow the finer slice grid; P pictures keep whole rows."""
+    frames = natural_frames(w, h)[:1] + [synth.desktop(w, h, 1), synth.desktop(w, h, 2), synth.noise(w, h, 7)]
+    enc = oracle.RefEncoder(w, h, 1)
+    enc.set_idr_slice_mbs(mbs)
+    idr_at = (0, 3)
+    ref = [enc.encode_bgra(f, i in idr_at, rc_mode=1, qp=27) for i, f in enumerate(frames)]
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=27, idr_slice_mbs=mbs) as s:
+        for i, f in enumerate(frames):
+            if i == 3:
+                s.flush()
+                s.request_idr()
+            s.submit(f)
+        s.flush()
+        got = s.take_frames()
+        grec = s.recon()
+    assert_same(got, ref, grec, enc.recon())
+    dec = avdec.decode_stream([g.data for g in got], quiet=True)
+    assert len(dec) == 4 and np.array_equal(dec[3][0], grec[0][:h, :w])
+    if mbs > 0:
+        n_idr_slices = sum(1 for i in range(len(got[0].data) - 4) if got[0].data[i:i + 3] == b"\x00\x00\x01" and (got[0].data[i + 3] & 31) == 5)
+        assert n_idr_slices == ((h + 15) // 16) * -(-((w + 15) // 16) // mbs)
+
+
+def test_idr_subrow_slices_striped_bit_exact():
+    w, h = 320, 192
+    frames = [synth.desktop(w, h, t) for t in range(3)]
+    enc = oracle.RefEncoder(w, h, 1)
+    enc.set_idr_slice_mbs(6)
+    enc.set_stripes(4)
+    ref, tabs = [], []
+    for i, f in enumerate(frames):
+        ref.append(enc.encode_bgra(f, i == 0, rc_mode=1, qp=30))
+        tabs.append(enc.stripe_table())
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=30, idr_slice_mbs=6, stripe_rows=4) as s:
+        for f in frames:
+            s.submit(f)
+        s.flush()
+        got = s.take_frames()
+    k = 0
+    for i, (au, tab) in enumerate(zip(ref, tabs)):
+        for b, (off, size, coded) in enumerate(tab):
+            if coded:
+                assert got[k].data == au[off: off + size], (i, b)
+                k += 1
+    assert k == len(got)
