@@ -50,8 +50,9 @@ def _u8p(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint8))
 
 
-def csc_nv12(bgra: np.ndarray, dst_w: int = 0, dst_h: int = 0, coded_w: int = 0, coded_h: int = 0):
-    """BGRA (H,W,4) uint8 -> (Y (coded_h,coded_w), UV (coded_h/2,coded_w)) per oracle/csc_ref.c."""
+def csc_nv12(bgra: np.ndarray, dst_w: int = 0, dst_h: int = 0, coded_w: int = 0, coded_h: int = 0, matrix: int = 0):
+    """BGRA (H,W,4) uint8 -> (Y (coded_h,coded_w), UV (coded_h/2,coded_w)) per oracle/csc_ref.c.
+    matrix 0 = BT.709 limited range (H.264 path), 1 = JFIF full-range BT.601 (JPEG stripe path)."""
     assert bgra.dtype == np.uint8 and bgra.ndim == 3 and bgra.shape[2] == 4
     bgra = np.ascontiguousarray(bgra)
     sh, sw = bgra.shape[:2]
@@ -61,10 +62,34 @@ def csc_nv12(bgra: np.ndarray, dst_w: int = 0, dst_h: int = 0, coded_w: int = 0,
     coded_h = coded_h or dst_h
     y = np.empty((coded_h, coded_w), np.uint8)
     uv = np.empty((coded_h // 2, coded_w), np.uint8)
-    rc = lib().b2v_ref_csc_nv12(_u8p(bgra), sw, sh, sw * 4, dst_w, dst_h, coded_w, coded_h, _u8p(y), _u8p(uv))
+    rc = lib().b2v_ref_csc_nv12_m(_u8p(bgra), sw, sh, sw * 4, dst_w, dst_h, coded_w, coded_h, _u8p(y), _u8p(uv), matrix)
     if rc != 0:
         raise ValueError(f"b2v_ref_csc_nv12 rc={rc}")
     return y, uv
+
+
+def jpeg_encode(y: np.ndarray, uv, width: int, height: int, quality: int) -> bytes:
+    """One baseline JFIF file per oracle/jpeg_ref.c.  y: (H',W') luma rows, uv: (H'/2, W') interleaved Cb,Cr rows or None (grey);
+    H', W' >= the next multiple of 16 (8 when grey) of height, width (padded by replication by the caller)."""
+    L = lib()
+    L.b2v_ref_jpeg_encode.restype = C.c_int64
+    L.b2v_ref_jpeg_encode.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    y = np.ascontiguousarray(y)
+    pitch = y.shape[1]
+    out = np.empty(y.size * 3 + 4096, np.uint8)
+    if uv is not None:
+        uv = np.ascontiguousarray(uv)
+        assert uv.shape[1] == pitch
+    n = L.b2v_ref_jpeg_encode(_u8p(y), _u8p(uv) if uv is not None else None, pitch, width, height, quality, _u8p(out))
+    return out[:n].tobytes()
+
+
+def jpeg_encode_bgra(bgra: np.ndarray, quality: int) -> bytes:
+    """oracle CSC (JFIF matrix, padded to a multiple of 16) + oracle JPEG: what one stripe of the JPEG mode must equal."""
+    h, w = bgra.shape[:2]
+    cw, ch = (w + 15) & ~15, (h + 15) & ~15
+    y, uv = csc_nv12(bgra, coded_w=cw, coded_h=ch, matrix=1)
+    return jpeg_encode(y, uv, w, h, quality)
 
 
 class RefEncoder:

@@ -116,9 +116,27 @@ static inline void fetch_bgr(const uint8_t* src, int stride, const tap_t* tx, co
  * out_y:  coded_h rows of coded_w bytes;  out_uv: coded_h/2 rows of coded_w bytes (Cb,Cr pairs)
  * dst_w/dst_h: visible (scaled) size, even; coded_w/coded_h >= dst, even.
  */
+/* matrix 0: BT.709 limited range (the H.264 path; the spec in the header).  matrix 1: JFIF full-range BT.601 (the JPEG stripe
+ * path, oracle/jpeg_ref.c): Y = (4899 R + 9617 G + 1868 B + 2^13) >> 14, Cb = 128 + ((-2765 SR - 5427 SG + 8191 SB + 2^15) >> 16),
+ * Cr = 128 + ((8191 SR - 6860 SG - 1332 SB + 2^15) >> 16); same scaling, padding and 2x2 box sum.  (0.5 is coded as 8191, not
+ * 8192: a saturated red or blue would otherwise reach 256; neutral greys still give exactly 128.) */
+static const int MATRIX[2][10] = {
+  { KYR, KYG, KYB, KUR, KUG, KUB, KVR, KVG, KVB, 16 },
+  { 4899, 9617, 1868, -2765, -5427, 8191, 8191, -6860, -1332, 0 } };
+
+int b2v_ref_csc_nv12_m(const uint8_t* bgra, int src_w, int src_h, int src_stride,
+                       int dst_w, int dst_h, int coded_w, int coded_h,
+                       uint8_t* out_y, uint8_t* out_uv, int matrix);
 int b2v_ref_csc_nv12(const uint8_t* bgra, int src_w, int src_h, int src_stride,
                      int dst_w, int dst_h, int coded_w, int coded_h,
                      uint8_t* out_y, uint8_t* out_uv) {
+  return b2v_ref_csc_nv12_m(bgra, src_w, src_h, src_stride, dst_w, dst_h, coded_w, coded_h, out_y, out_uv, 0);
+}
+int b2v_ref_csc_nv12_m(const uint8_t* bgra, int src_w, int src_h, int src_stride,
+                       int dst_w, int dst_h, int coded_w, int coded_h,
+                       uint8_t* out_y, uint8_t* out_uv, int matrix) {
+  if (matrix < 0 || matrix > 1) return -1;
+  const int* M = MATRIX[matrix];
   if (src_w < 2 || src_h < 2 || (dst_w & 1) || (dst_h & 1) || (coded_w & 1) || (coded_h & 1) ||
       coded_w < dst_w || coded_h < dst_h)
     return -1;
@@ -138,11 +156,11 @@ int b2v_ref_csc_nv12(const uint8_t* bgra, int src_w, int src_h, int src_stride,
           int bgr[3];
           fetch_bgr(bgra, src_stride, tx, ty, px, py, bgr);
           out_y[(size_t)(y + dy) * coded_w + x + dx] =
-              (uint8_t)(16 + ((KYR * bgr[2] + KYG * bgr[1] + KYB * bgr[0] + (1 << 13)) >> 14));
+              (uint8_t)(M[9] + ((M[0] * bgr[2] + M[1] * bgr[1] + M[2] * bgr[0] + (1 << 13)) >> 14));
           sb += bgr[0]; sg += bgr[1]; sr += bgr[2];
         }
-      out_uv[(size_t)(y >> 1) * coded_w + x]     = (uint8_t)(128 + asr(KUR * sr + KUG * sg + KUB * sb + (1 << 15), 16));
-      out_uv[(size_t)(y >> 1) * coded_w + x + 1] = (uint8_t)(128 + asr(KVR * sr + KVG * sg + KVB * sb + (1 << 15), 16));
+      out_uv[(size_t)(y >> 1) * coded_w + x]     = (uint8_t)(128 + asr(M[3] * sr + M[4] * sg + M[5] * sb + (1 << 15), 16));
+      out_uv[(size_t)(y >> 1) * coded_w + x + 1] = (uint8_t)(128 + asr(M[6] * sr + M[7] * sg + M[8] * sb + (1 << 15), 16));
     }
   }
   free(tx); free(ty);

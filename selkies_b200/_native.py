@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb2video.so")
 B2V_OK, B2V_EINVAL, B2V_ECUDA, B2V_ENOMEM, B2V_ESTATE, B2V_ETIMEOUT = 0, -1, -2, -3, -4, -5
 B2V_RC_CBR, B2V_RC_CQP = 0, 1
 B2V_HDR_NONE, B2V_HDR_PIXELFLUX = 0, 1
-B2V_FLAG_SPS_EVERY_IDR, B2V_FLAG_NO_ENCODE, B2V_FLAG_TIMING, B2V_FLAG_DEVICE_TIMER, B2V_FLAG_TIMING_CSC = 1, 2, 4, 8, 16
+B2V_FLAG_SPS_EVERY_IDR, B2V_FLAG_NO_ENCODE, B2V_FLAG_TIMING, B2V_FLAG_DEVICE_TIMER, B2V_FLAG_TIMING_CSC, B2V_FLAG_JPEG = 1, 2, 4, 8, 16, 32
 
 
 class B2VSettings(C.Structure):

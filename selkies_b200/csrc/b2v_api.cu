@@ -27,6 +27,7 @@
 #include "../../include/b2video.h"
 #include "b2v_internal.h"
 #include "h264_encoder.h"
+#include "jpeg.h"
 
 using namespace b2v;
 
@@ -102,8 +103,10 @@ struct Session {
   Tap *d_tx = nullptr, *d_ty = nullptr;
   // current-frame NV12 (coded size)
   uint8_t* d_cur = nullptr;
-  // encoder
+  // encoder: H.264 (enc) or, with B2V_FLAG_JPEG, JPEG stripes (jenc)
   Encoder* enc = nullptr;
+  JpegEncoder* jenc = nullptr;
+  bool jpeg = false;
   // output ring
   uint8_t* d_au[kMaxSlots] = {};
   uint8_t* h_out[kMaxSlots] = {};
@@ -163,7 +166,22 @@ int alloc_geometry(Session* s) {
     CK(cudaMemcpy(s->d_tx, tx.data(), sizeof(Tap) * s->dst_w, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_ty, ty.data(), sizeof(Tap) * s->dst_h, cudaMemcpyHostToDevice));
   }
-  if (s->encode) {
+  if (s->encode && s->jpeg) {
+    JpegConfig jc{};
+    jc.width = s->dst_w; jc.height = s->dst_h; jc.coded_w = s->coded_w; jc.coded_h = s->coded_h;
+    jc.stripe_rows = s->cfg.stripe_rows > 0 ? s->cfg.stripe_rows : (s->coded_h / 16 + 7) / 8;       // default: about 8 stripes
+    jc.quality = s->cfg.crf > 0 ? s->cfg.crf : 60; jc.paint_quality = s->cfg.paintover_crf > 0 ? s->cfg.paintover_crf : 90;
+    jc.paint_trigger = s->cfg.paintover_trigger_frames > 0 ? s->cfg.paintover_trigger_frames : 0;
+    int rc = jpeg_create(&jc, &s->jenc);
+    if (rc) return fail(rc, "jpeg_create failed: %s", jpeg_last_error());
+    s->au_cap = jpeg_au_capacity(s->jenc);
+    s->au_data_off = jpeg_au_data_offset(s->jenc);
+    s->n_bands = jpeg_stripe_count(s->jenc);
+    for (int i = 0; i < s->n_slots; i++) {
+      CK(cudaMalloc((void**)&s->d_au[i], s->au_cap));
+      CK(cudaHostAlloc((void**)&s->h_out[i], s->au_cap + kOutHead, cudaHostAllocDefault));
+    }
+  } else if (s->encode) {
     EncoderConfig ec{};
     ec.width = s->dst_w; ec.height = s->dst_h; ec.coded_w = s->coded_w; ec.coded_h = s->coded_h;
     ec.slice_rows = s->cfg.slice_rows > 0 ? s->cfg.slice_rows : 1;
@@ -201,6 +219,7 @@ void free_geometry(Session* s) {
   if (s->d_ty) cudaFree(s->d_ty);
   s->d_cur = nullptr; s->d_tx = nullptr; s->d_ty = nullptr;
   if (s->enc) { encoder_destroy(s->enc); s->enc = nullptr; }
+  if (s->jenc) { jpeg_destroy(s->jenc); s->jenc = nullptr; }
 }
 
 CscParams csc_params(Session* s, const uint8_t* d_bgra, int stride, uint8_t* d_nv12, const void* tmap = nullptr) {
@@ -210,6 +229,7 @@ CscParams csc_params(Session* s, const uint8_t* d_bgra, int stride, uint8_t* d_n
   p.dst_w = s->dst_w; p.dst_h = s->dst_h; p.coded_w = s->coded_w; p.coded_h = s->coded_h;
   p.out_y = d_nv12; p.out_uv = d_nv12 + (size_t)s->coded_w * s->coded_h;
   p.tx = s->d_tx; p.ty = s->d_ty;
+  p.matrix = s->jpeg ? 1 : 0;           // JPEG stripes carry JFIF (full-range BT.601) colour, H.264 BT.709 limited range
   return p;
 }
 
@@ -302,7 +322,7 @@ void output_loop(Session* s) {
       std::vector<BandEntry> tab(s->n_bands);
       memcpy(tab.data(), s->h_out[j.out_idx] + sizeof(AuHeader), sizeof(BandEntry) * s->n_bands);
       uint8_t* au = s->h_out[j.out_idx] + s->au_data_off;
-      const int rows = s->cfg.stripe_rows * 16;
+      const int rows = (s->jpeg ? jpeg_stripe_rows(s->jenc) : s->cfg.stripe_rows) * 16;
       int delivered_bytes = 0;
       for (int b = 0; b < s->n_bands; b++) {
         const BandEntry& be = tab[b];
@@ -310,7 +330,13 @@ void output_loop(Session* s) {
         const int y0 = b * rows, bh = (y0 + rows <= j.hdr_h) ? rows : j.hdr_h - y0;
         b2v_frame f{};
         f.data = au + be.off; f.size = be.size;
-        if (s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
+        if (s->jpeg && s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
+          // JPEG stripe: frame_id u16be | y_start u16be | JFIF file (the reference prepends 03 00, selkies.py:3118; the client reads the
+          // frame id at offset 2 and y_start at offset 4, selkies-ws-core.js:3166-3172)
+          uint8_t* h = au + be.off - 4;
+          h[0] = (uint8_t)(j.frame_id >> 8); h[1] = (uint8_t)j.frame_id; h[2] = (uint8_t)(y0 >> 8); h[3] = (uint8_t)y0;
+          f.data = h; f.size += 4;
+        } else if (s->cfg.header_mode == B2V_HDR_PIXELFLUX) {
           uint8_t* h = au + be.off - 10;
           h[0] = 0x04; h[1] = j.is_key ? 1 : 0;
           h[2] = (uint8_t)(j.frame_id >> 8); h[3] = (uint8_t)j.frame_id;
@@ -417,7 +443,16 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
   if (ev) cudaEventRecord(ev[1], s->st_enc);
   if (in_slot >= 0) CKS(cudaEventRecord(s->ev_csc[in_slot], s->st_enc));
   CKS(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
-  if (s->encode) {
+  if (s->encode && s->jpeg) {
+    nl += jpeg_encode(s->jenc, s->d_cur, s->d_au[out_idx], j.is_key, s->st_enc);
+    CKS(cudaEventRecord(s->ev_enc[out_idx], s->st_enc));
+    CKS(cudaStreamWaitEvent(s->st_out, s->ev_enc[out_idx], 0));
+    size_t first = s->au_cap < kFirstChunk ? s->au_cap : kFirstChunk;
+    CKS(cudaMemcpyAsync(s->h_out[out_idx], s->d_au[out_idx], first, cudaMemcpyDeviceToHost, s->st_out));
+    CKS(cudaEventRecord(s->ev_out[out_idx], s->st_out));
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->stats.d2h_bytes += (int64_t)first;
+  } else if (s->encode) {
     fp.cur = s->d_cur; fp.au = s->d_au[out_idx]; fp.ev = s->timing_csc_only ? nullptr : ev; fp.csc_ts = cp.ts;
     fp.st_pack = fp.ev ? nullptr : s->st_pack;      // per-stage events need the serial schedule
     nl += encoder_encode(s->enc, &fp, s->st_enc);
@@ -491,6 +526,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   s->cfg = *cfg; s->device = cfg->device;
   s->src_w = sw; s->src_h = sh; s->dst_w = dw; s->dst_h = dh;
   s->encode = !(cfg->flags & B2V_FLAG_NO_ENCODE);
+  s->jpeg = (cfg->flags & B2V_FLAG_JPEG) != 0;
   s->timing = (cfg->flags & (B2V_FLAG_TIMING | B2V_FLAG_TIMING_CSC)) != 0;
   s->timing_csc_only = s->timing && !(cfg->flags & B2V_FLAG_TIMING);
   s->n_slots = cfg->ring_slots > 0 ? cfg->ring_slots : 4;
@@ -748,7 +784,7 @@ int b2v_csc_nv12(void* h, const void* bgra, int32_t stride, void* nv12) {
 int b2v_get_recon(void* h, void* nv12) {
   Session* s = (Session*)h;
   if (!s || !nv12) return fail(B2V_EINVAL, "null argument");
-  if (!s->encode) return fail(B2V_ESTATE, "session was created with B2V_FLAG_NO_ENCODE");
+  if (!s->encode || !s->enc) return fail(B2V_ESTATE, "no H.264 reconstruction in this session (B2V_FLAG_NO_ENCODE / B2V_FLAG_JPEG)");
   int rc = b2v_flush(h);
   if (rc) return rc;
   std::lock_guard<std::mutex> sub(s->submit_mu);

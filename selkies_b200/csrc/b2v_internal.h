@@ -24,6 +24,7 @@ struct CscParams {
   const Tap* ty;        // dst_h taps
   unsigned long long* ts; // null, or {min block-start, max block-end} %globaltimer stamps of this launch (B2V_FLAG_TIMING)
   const void* tmap;       // null, or the device-resident CUtensorMap of `src` (csc_make_tensor_map): enables the TMA kernel
+  int matrix;             // 0 = BT.709 limited range (H.264 path), 1 = JFIF full-range BT.601 (JPEG stripe path)
 };
 
 // returns number of kernel launches issued (1)

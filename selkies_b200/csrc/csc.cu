@@ -67,18 +67,16 @@ __device__ __forceinline__ void st_stream(uint8_t* p, unsigned v) {
 }
 
 // pixel word: byte0 = B, byte1 = G, byte2 = R, byte3 = A (ignored: coefficient 0)
-constexpr int pack16(int lo, int hi) { return (int)(((unsigned)lo & 0xffffu) | ((unsigned)hi << 16)); }
-constexpr int CY_LO = pack16(KYB, KYG), CY_HI = pack16(KYR, 0);
-constexpr int CU_LO = pack16(KUB, KUG), CU_HI = pack16(KUR, 0);
-constexpr int CV_LO = pack16(KVB, KVG), CV_HI = pack16(KVR, 0);
-constexpr int Y_SEED = (16 << 14) + (1 << 13);
+__host__ __device__ constexpr int pack16(int lo, int hi) { return (int)(((unsigned)lo & 0xffffu) | ((unsigned)hi << 16)); }
+// Colour matrices (14-bit coefficients).  0: BT.709 limited range, the H.264 path.  1: JFIF full-range BT.601, the
+// JPEG stripe path (0.5 is coded as 8191 so that a saturated red / blue stays at 255; greys still give exactly 128) — the same
+// numbers as oracle/csc_ref.c MATRIX[].
+template <int M> struct Mx;
+template <> struct Mx<0> { static constexpr int YR = KYR, YG = KYG, YB = KYB, UR = KUR, UG = KUG, UB = KUB, VR = KVR, VG = KVG, VB = KVB, YOFF = 16; };
+template <> struct Mx<1> { static constexpr int YR = 4899, YG = 9617, YB = 1868, UR = -2765, UG = -5427, UB = 8191, VR = 8191, VG = -6860, VB = -1332, YOFF = 0; };
+__device__ const int c_mx[2][10] = {{KYR, KYG, KYB, KUR, KUG, KUB, KVR, KVG, KVB, 16}, {4899, 9617, 1868, -2765, -5427, 8191, 8191, -6860, -1332, 0}};
+constexpr int Y_SEED = (16 << 14) + (1 << 13);      // matrix 0
 constexpr int C_SEED = (128 << 16) + (1 << 15);
-// Luma with the coefficients scaled by 4 (all three are positive and 4*KYG = 40256 still fits an UNSIGNED 16-bit dp2a lane):
-// 4*(k.px) + 4*seed puts (k.px + seed) >> 14 into byte 2 of the accumulator, exactly (the factor 4 is exact), so the result is
-// picked up by the same byte permute that packs four pixels — no shift instruction per pixel.  Chroma (>> 16) sits in byte 2 already.
-constexpr int CY4_LO = pack16(4 * KYB, 4 * KYG), CY4_HI = pack16(4 * KYR, 0);
-constexpr unsigned Y4_SEED = 4u * (unsigned)Y_SEED;
-static_assert(4 * KYG < 65536 && 4 * (KYR + KYG + KYB) * 255 + 4 * Y_SEED < (1 << 24), "luma accumulator must stay below byte 3");
 
 __device__ __forceinline__ unsigned dp2a_lo_u(unsigned coef, unsigned px, unsigned acc) {
   unsigned d; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(px), "r"(acc)); return d;
@@ -86,8 +84,15 @@ __device__ __forceinline__ unsigned dp2a_lo_u(unsigned coef, unsigned px, unsign
 __device__ __forceinline__ unsigned dp2a_hi_u(unsigned coef, unsigned px, unsigned acc) {
   unsigned d; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(px), "r"(acc)); return d;
 }
+// Luma with the coefficients scaled by 4 (all three are positive and 4*KYG still fits an UNSIGNED 16-bit dp2a lane):
+// 4*(k.px) + 4*seed puts (k.px + seed) >> 14 into byte 2 of the accumulator, exactly (the factor 4 is exact), so the result is
+// picked up by the same byte permute that packs four pixels — no shift instruction per pixel.  Chroma (>> 16) sits in byte 2 already.
+template <int M>
 __device__ __forceinline__ unsigned luma_b2(unsigned px) {      // Y in byte 2
-  return dp2a_hi_u((unsigned)CY4_HI, px, dp2a_lo_u((unsigned)CY4_LO, px, Y4_SEED));
+  using X = Mx<M>;
+  static_assert(4 * X::YG < 65536 && 4 * (X::YR + X::YG + X::YB) * 255 + 4 * ((X::YOFF << 14) + (1 << 13)) < (1 << 24), "luma accumulator must stay below byte 3");
+  constexpr unsigned lo = (unsigned)pack16(4 * X::YB, 4 * X::YG), hi = (unsigned)pack16(4 * X::YR, 0), seed = 4u * (unsigned)((X::YOFF << 14) + (1 << 13));
+  return dp2a_hi_u(hi, px, dp2a_lo_u(lo, px, seed));
 }
 __device__ __forceinline__ int chroma_acc(int clo, int chi, unsigned px, int acc) {
   return dp2a_hi(chi, px, dp2a_lo(clo, px, acc));
@@ -98,9 +103,12 @@ __device__ __forceinline__ unsigned pack4_b2(unsigned a, unsigned b, unsigned c,
 }
 
 // 4 px x 2 rows -> Y (two u32) + CbCr (one u32 = Cb0 Cr0 Cb1 Cr1)
+template <int M = 0>
 __device__ __forceinline__ void convert_quad(const uint4& a, const uint4& b, unsigned& y0, unsigned& y1, unsigned& uv) {
-  y0 = pack4_b2(luma_b2(a.x), luma_b2(a.y), luma_b2(a.z), luma_b2(a.w));
-  y1 = pack4_b2(luma_b2(b.x), luma_b2(b.y), luma_b2(b.z), luma_b2(b.w));
+  using X = Mx<M>;
+  constexpr int CU_LO = pack16(X::UB, X::UG), CU_HI = pack16(X::UR, 0), CV_LO = pack16(X::VB, X::VG), CV_HI = pack16(X::VR, 0);
+  y0 = pack4_b2(luma_b2<M>(a.x), luma_b2<M>(a.y), luma_b2<M>(a.z), luma_b2<M>(a.w));
+  y1 = pack4_b2(luma_b2<M>(b.x), luma_b2<M>(b.y), luma_b2<M>(b.z), luma_b2<M>(b.w));
   int u0 = chroma_acc(CU_LO, CU_HI, b.y, chroma_acc(CU_LO, CU_HI, b.x, chroma_acc(CU_LO, CU_HI, a.y, chroma_acc(CU_LO, CU_HI, a.x, C_SEED))));
   int v0 = chroma_acc(CV_LO, CV_HI, b.y, chroma_acc(CV_LO, CV_HI, b.x, chroma_acc(CV_LO, CV_HI, a.y, chroma_acc(CV_LO, CV_HI, a.x, C_SEED))));
   int u1 = chroma_acc(CU_LO, CU_HI, b.w, chroma_acc(CU_LO, CU_HI, b.z, chroma_acc(CU_LO, CU_HI, a.w, chroma_acc(CU_LO, CU_HI, a.z, C_SEED))));
@@ -110,7 +118,7 @@ __device__ __forceinline__ void convert_quad(const uint4& a, const uint4& b, uns
 
 // ---- fast path ---------------------------------------------------------------------------
 // grid.x covers 4-px quads of a row, grid.y strides over groups of U row pairs.
-template <int U, bool EF>
+template <int U, bool EF, int M = 0>
 __global__ void __launch_bounds__(256) csc_bgra_nv12_fast(CscParams p, int quads, int pairs) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long pol = EF ? policy_evict_first() : 0ull;
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(256) csc_bgra_nv12_fast(CscParams p, int quads
       int pr = pr0 + u;
       if (pr < pairs) {
         unsigned y0, y1, uv;
-        convert_quad(a[u], b[u], y0, y1, uv);
+        convert_quad<M>(a[u], b[u], y0, y1, uv);
         st_stream(p.out_y + (size_t)(2 * pr) * p.coded_w + q * 4, y0);
         st_stream(p.out_y + (size_t)(2 * pr + 1) * p.coded_w + q * 4, y1);
         st_stream(p.out_uv + (size_t)pr * p.coded_w + q * 4, uv);
@@ -292,6 +300,7 @@ __global__ void __launch_bounds__(256) csc_bgra_nv12_general(CscParams p) {
   int bx = blockIdx.x * blockDim.x + threadIdx.x;   // 2x2 block column
   int by = blockIdx.y * blockDim.y + threadIdx.y;
   if (bx * 2 >= p.coded_w || by * 2 >= p.coded_h) return;
+  const int* mx = c_mx[p.matrix];
   int sb = 0, sg = 0, sr = 0;
   unsigned yy[4];
 #pragma unroll
@@ -299,11 +308,11 @@ __global__ void __launch_bounds__(256) csc_bgra_nv12_general(CscParams p) {
     int x = min(bx * 2 + (k & 1), p.dst_w - 1), y = min(by * 2 + (k >> 1), p.dst_h - 1);
     int B, G, R;
     fetch_bgr(p, x, y, B, G, R);
-    yy[k] = (unsigned)(KYR * R + KYG * G + KYB * B + Y_SEED) >> 14;
+    yy[k] = (unsigned)(mx[0] * R + mx[1] * G + mx[2] * B + (mx[9] << 14) + (1 << 13)) >> 14;
     sb += B; sg += G; sr += R;
   }
-  unsigned cb = (unsigned)(KUR * sr + KUG * sg + KUB * sb + C_SEED) >> 16;
-  unsigned cr = (unsigned)(KVR * sr + KVG * sg + KVB * sb + C_SEED) >> 16;
+  unsigned cb = (unsigned)(mx[3] * sr + mx[4] * sg + mx[5] * sb + C_SEED) >> 16;
+  unsigned cr = (unsigned)(mx[6] * sr + mx[7] * sg + mx[8] * sb + C_SEED) >> 16;
   *(uint16_t*)(p.out_y + (size_t)(by * 2) * p.coded_w + bx * 2) = (uint16_t)(yy[0] | (yy[1] << 8));
   *(uint16_t*)(p.out_y + (size_t)(by * 2 + 1) * p.coded_w + bx * 2) = (uint16_t)(yy[2] | (yy[3] << 8));
   *(uint16_t*)(p.out_uv + (size_t)by * p.coded_w + bx * 2) = (uint16_t)(cb | (cr << 8));
@@ -356,6 +365,7 @@ __global__ void __launch_bounds__(SC_THREADS) csc_bgra_nv12_scaled(CscParams p, 
   const int bx = tid % (SC_TW / 2), by = tid / (SC_TW / 2);
   const int ox = ox0 + 2 * bx, oy = oy0 + 2 * by;
   if (ox >= p.coded_w || oy >= p.coded_h) return;
+  const int* mx = c_mx[p.matrix];
   int sb = 0, sg = 0, sr = 0;
   unsigned yy[4];
 #pragma unroll
@@ -364,11 +374,11 @@ __global__ void __launch_bounds__(SC_THREADS) csc_bgra_nv12_scaled(CscParams p, 
     const Tap ax = p.tx[x], ay = p.ty[y];
     int B, G, R;
     blend_px(&sc_tile[(ay.i0 - ys0) * fw_cap], &sc_tile[(ay.i1 - ys0) * fw_cap], ax.i0 - xs0, ax.i1 - xs0, ax.f, ay.f, B, G, R);
-    yy[k] = (unsigned)(KYR * R + KYG * G + KYB * B + Y_SEED) >> 14;
+    yy[k] = (unsigned)(mx[0] * R + mx[1] * G + mx[2] * B + (mx[9] << 14) + (1 << 13)) >> 14;
     sb += B; sg += G; sr += R;
   }
-  const unsigned cb = (unsigned)(KUR * sr + KUG * sg + KUB * sb + C_SEED) >> 16;
-  const unsigned cr = (unsigned)(KVR * sr + KVG * sg + KVB * sb + C_SEED) >> 16;
+  const unsigned cb = (unsigned)(mx[3] * sr + mx[4] * sg + mx[5] * sb + C_SEED) >> 16;
+  const unsigned cr = (unsigned)(mx[6] * sr + mx[7] * sg + mx[8] * sb + C_SEED) >> 16;
   *reinterpret_cast<uint16_t*>(p.out_y + (size_t)oy * p.coded_w + ox) = (uint16_t)(yy[0] | (yy[1] << 8));
   *reinterpret_cast<uint16_t*>(p.out_y + (size_t)(oy + 1) * p.coded_w + ox) = (uint16_t)(yy[2] | (yy[3] << 8));
   *reinterpret_cast<uint16_t*>(p.out_uv + (size_t)(oy >> 1) * p.coded_w + ox) = (uint16_t)(cb | (cr << 8));
@@ -445,7 +455,7 @@ int launch_csc(const CscParams& p, int sm_count, cudaStream_t st) {
   const bool fast = p.tx == nullptr && p.ty == nullptr && p.dst_w == p.src_w && p.dst_h == p.src_h && p.coded_w == p.dst_w &&
                     (p.coded_w % 4) == 0 && (p.src_stride % 16) == 0 && ((uintptr_t)p.src % 16) == 0 &&
                     ((uintptr_t)p.out_y % 4) == 0 && ((uintptr_t)p.out_uv % 4) == 0;
-  if (fast && g_csc_tma && p.tmap && (p.src_h % 2) == 0 && p.coded_h >= p.src_h) {
+  if (fast && p.matrix == 0 && g_csc_tma && p.tmap && (p.src_h % 2) == 0 && p.coded_h >= p.src_h) {
     const int stages = g_csc_tma_stages, smem = stages * TMA_TILE_BYTES;
     static int attr_smem = 0;
     if (smem > attr_smem) { cudaFuncSetAttribute(csc_bgra_nv12_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_smem = smem; }
@@ -467,7 +477,9 @@ int launch_csc(const CscParams& p, int sm_count, cudaStream_t st) {
     if (gy > groups) gy = groups;
     if (gy > 65535) gy = 65535;
     dim3 grid(gx, gy);
-    if (g_csc_evict_first) {
+    if (p.matrix == 1) {
+      csc_bgra_nv12_fast<2, false, 1><<<grid.y == (unsigned)gy && U == 2 ? grid : dim3(gx, (pairs + 1) / 2), block, 0, st>>>(p, quads, pairs);
+    } else if (g_csc_evict_first) {
       switch (U) {
         case 1: csc_bgra_nv12_fast<1, true><<<grid, block, 0, st>>>(p, quads, pairs); break;
         case 2: csc_bgra_nv12_fast<2, true><<<grid, block, 0, st>>>(p, quads, pairs); break;

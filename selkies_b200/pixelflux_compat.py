@@ -192,11 +192,10 @@ class ScreenCapture:
         with self._lock:
             if self._h is not None:
                 raise RuntimeError("capture already running")
-            if int(getattr(settings, "output_mode", 1)) != 1:
-                raise ValueError("output_mode=0 (JPEG stripes) is not implemented by the B200 pipeline; use output_mode=1 (H.264)")
+            jpeg = int(getattr(settings, "output_mode", 1)) == 0        # the reference's "jpeg" encoder (selkies.py:3209-3212)
             if not callable(callback):
                 raise TypeError("callback must be callable or a StripeCallback")
-            if bool(getattr(settings, "h264_fullcolor", False)):
+            if not jpeg and bool(getattr(settings, "h264_fullcolor", False)):
                 raise ValueError("h264_fullcolor (4:4:4) is not implemented; the pipeline encodes 4:2:0")
             w, h = int(settings.capture_width), int(settings.capture_height)
             w -= w & 1
@@ -230,6 +229,15 @@ class ScreenCapture:
                     mbh = ((int(s.dst_h) or h) + 15) // 16
                     rows = -(-mbh // 8)
                 s.stripe_rows = -(-rows // sl) * sl
+            if jpeg:
+                # JPEG stripes: each changed stripe is one JFIF file behind frame_id | y_start; unchanged stripes are not sent, a
+                # stripe static for paint_over_trigger_frames pictures is sent once more at paint_over_jpeg_quality
+                s.flags |= N.B2V_FLAG_JPEG
+                s.rc_mode = N.B2V_RC_CQP
+                s.crf = int(getattr(settings, "jpeg_quality", 60))
+                s.paintover_crf = int(getattr(settings, "paint_over_jpeg_quality", 90))
+                s.paintover_trigger_frames = int(getattr(settings, "paint_over_trigger_frames", 15) or 0) if bool(getattr(settings, "use_paint_over_quality", False)) else 0
+                s.stripe_rows = int(getattr(settings, "h264_stripe_rows", 0) or 0)
             self._user_cb = callback
             self._cb_native = N.FRAME_CB(self._on_frame)
             handle = C.c_void_p()

@@ -57,7 +57,7 @@ def test_screen_capture_contract_and_parity():
         assert hdr[0] == 0x04 and hdr[1] == (1 if i == 0 else 0) and int.from_bytes(hdr[2:4], "big") == i
     with pytest.raises(ValueError):
         bad = CaptureSettings()
-        bad.output_mode = 0
+        bad.h264_fullcolor = True                                # 4:4:4 is the one CaptureSettings switch this pipeline refuses
         ScreenCapture().start_capture(bad, cb)
 
 
