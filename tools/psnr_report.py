@@ -14,6 +14,9 @@ from tests import synth
 def content(name, w, h, n):
     if name == "desktop_scroll":
         return [synth.desktop(w, h, t) for t in range(n)]
+    if name == "bench_cycle16":               # bench.py's workload: 16 distinct pictures cycled (the scroll restarts every 16 pictures)
+        fr = [synth.desktop(w, h, t) for t in range(16)]
+        return [fr[t % 16] for t in range(n)]
     if name == "bars_box":
         return [synth.bars(w, h, t) for t in range(n)]
     if name == "gradient_pan":
@@ -57,8 +60,15 @@ def run(w, h, name, kbps, fps, n):
         ps[i] = (avdec.psnr(Y, sy), avdec.psnr(U, suv[:, 0::2]), avdec.psnr(V, suv[:, 1::2]))
     sizes = [len(g.data) for g in got]
     tl = [i for i in ps if i != 0 or n == 1]
+    win = int(fps)
+    tb = kbps * 1000.0 / fps / 8.0             # target bytes per picture
+    windows = [sum(sizes[i:i + win]) / (tb * win) for i in range(0, max(1, n - win + 1))]
+    qps = [g.qp for g in got]
     return {"w": w, "h": h, "content": name, "target_kbps": kbps, "fps": fps, "frames": n,
-            "achieved_kbps_steady": float(np.mean([sizes[i] for i in tail]) * 8 * fps / 1000), "idr_bytes": sizes[0],
+            "achieved_kbps_steady": float(np.mean([sizes[i] for i in tail]) * 8 * fps / 1000),
+            "achieved_over_target_steady": float(np.mean([sizes[i] for i in tail]) / tb),
+            "worst_1s_window_over_target": float(max(windows)), "worst_1s_window_after_the_first_second": float(max(windows[win:])) if len(windows) > win else None,
+            "qp_pinned": "max" if min(qps[n // 2:]) >= 51 else "min" if max(qps[n // 2:]) <= 10 else None, "idr_bytes": sizes[0],
             "psnr_y_steady": float(np.mean([ps[i][0] for i in tl])), "psnr_u_steady": float(np.mean([ps[i][1] for i in tl])),
             "psnr_v_steady": float(np.mean([ps[i][2] for i in tl])), "psnr_y_idr": ps[0][0],
             "qp_first_last": [got[0].qp, got[-1].qp], "qp_steady_mean": float(np.mean([got[i].qp for i in tail]))}
@@ -68,13 +78,15 @@ def main():
     os.makedirs("gpurun_out", exist_ok=True)
     rows = []
     for (w, h) in [(1920, 1080), (3840, 2160)]:
-        for name in ["desktop_scroll", "bars_box", "gradient_pan", "static_desktop"]:
+        for name in ["desktop_scroll", "bench_cycle16", "bars_box", "gradient_pan", "static_desktop"]:
             for kbps in [8000, 20000, 50000, 100000]:
-                r = run(w, h, name, kbps, 60.0, 120 if w == 1920 else 90)
+                r = run(w, h, name, kbps, 60.0, 240 if w == 1920 else 180)
                 rows.append(r)
                 print(json.dumps(r), flush=True)
     out = {"x264_comparator": shutil.which("x264") or "absent", "gst_launch": shutil.which("gst-launch-1.0") or "absent",
-           "rate_control": "CBR (settings.py:49 range 1-100 Mbps)", "rows": rows}
+           "rate_control": "CBR (settings.py:49 range 1-100 Mbps); bucket + ratio controller, QP 10..51, feedback two pictures late (DESIGN.md 5.6)",
+           "reading": "achieved_over_target_steady is over the second half of the run; qp_pinned = the controller sat at its limit there (content cannot use / cannot fit the budget)",
+           "rows": rows}
     json.dump(out, open("gpurun_out/psnr_report.json", "w"), indent=1)
 
 
