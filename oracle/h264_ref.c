@@ -118,7 +118,7 @@ typedef struct {
   int stripe_fn[MAX_STRIPES];
   int32_t stripe_tab[MAX_STRIPES][3];   /* last picture: byte offset, size, coded flag */
   uint8_t sps_band[2][64]; int sps_band_len[2];   /* [0] regular band, [1] last band (may be shorter / cropped) */
-  int no_i4, no_tpred;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED, read once at create) */
+  int no_i4, no_tpred, no_refine_cap;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED / B2V_REF_NO_REFINE_CAP, read once at create) */
 } enc_t;
 
 static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -606,6 +606,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
 
 /* ------------------------------------------------------------------ inter macroblock (8.4) */
 #define ME_EARLY_SAD_PER_LAMBDA 96
+#define ME_REFINE_MAX_SAD 8192             /* no sub-sample refinement of a full-sample match this bad */
 #define ME_PRED_SAD_FACTOR 4
 #define ME_FRAC_PENALTY_BITS 4   /* fractional vectors pay 4 extra bits: they cost more mvd bits than the zero-relative estimate sees */
 static int se_bits(int v) { unsigned c = v > 0 ? 2u * v - 1 : (unsigned)(-2 * v); int len = 0; c += 1; while ((c >> len) > 1) len++; return 2 * len + 1; }
@@ -722,7 +723,8 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   const int sad_int = (int)(best >> 11) - lambda * (se_bits(4 * bdx) + se_bits(4 * bdy));
   /* a predictor hit whose previous vector was full-sample is not refined again: the previous refinement already preferred it */
   const int pred_frac = pred_hit && ((prev_mvx | prev_mvy) & 3);
-  if ((search || pred_frac) && iabs(bdx) <= 13 && iabs(bdy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda) {
+  /* ... nor when it is hopeless (mean absolute difference of 32 per sample and more: new content, nothing to polish) */
+  if ((search || pred_frac) && iabs(bdx) <= 13 && iabs(bdy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda && (e->no_refine_cap || sad_int < ME_REFINE_MAX_SAD)) {
     int16_t b1[22][17];
     const int ox = 16 + bdx, oy = 16 + bdy;
     for (int v = -3; v <= 18; v++) for (int u = -3; u <= 18; u++) Gp[v + 3][u + 3] = win[oy + v][ox + u];
@@ -1149,7 +1151,7 @@ void* b2v_ref_enc_create(int width, int height, int slice_rows) {
   e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
   e->fb[0].qp = e->fb[1].qp = -1; e->paint_burst = 1;
   e->seg_cols = e->slice_rows == 1 ? auto_seg_cols(e->mbw, e->mbh) : 0;
-  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL;
+  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL; e->no_refine_cap = getenv("B2V_REF_NO_REFINE_CAP") != NULL;
   write_param_sets(e);
   return e;
 }

@@ -36,6 +36,7 @@ struct alignas(16) InterSm {      // one per warp; the 16-byte size padding keep
 
 constexpr int ME_PRED_SAD_FACTOR = 4;      // temporal predictor accepted up to 4x the early-termination threshold (and only as a strict local minimum)
 constexpr int ME_FRAC_PENALTY_BITS = 4;   // fractional vectors pay 4 extra bits in the refinement cost
+constexpr int ME_REFINE_MAX_SAD = 8192;   // no sub-sample refinement of a full-sample match this bad
 
 // Table 8-12 as data: every fractional position is one plane sample or the rounded average of two.
 // entry = p1 | dx1<<2 | dy1<<3 | p2<<4 | dx2<<7 | dy2<<8, planes 0 G (full sample), 1 b, 2 h, 3 j, p2 = 4: none
@@ -233,7 +234,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   // quantisation noise of this QP (same threshold as the zero-motion early termination)
   const int sad_int = (searched || pred_hit) ? (int)(best >> 11) - lambda * (se_bits_dev(4 * dx) + se_bits_dev(4 * dy)) : 0;
   // a predictor hit whose previous vector was full-sample is not refined again: the previous refinement already preferred it
-  const bool refine = (searched || pred_frac) && abs(dx) <= 13 && abs(dy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda;
+  // ... and not when the full-sample match is hopeless (mean absolute difference >= 32 per sample: new content, nothing to polish —
+  // the refinement is a third of the work of a searched macroblock and bought 0 % bits on such pictures)
+  const bool refine = (searched || pred_frac) && abs(dx) <= 13 && abs(dy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda && sad_int < ME_REFINE_MAX_SAD;
   const int ox = dxi, oy = dyi;                                        // window coordinates of the full-sample position
   if (refine) {
     // half-sample planes
