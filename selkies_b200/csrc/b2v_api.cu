@@ -418,7 +418,10 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
     j.capture_ns = capture_ns;
     int ifps = (int)s->fps; if (ifps < 1) ifps = 1;
     j.pts = (int64_t)j.frame_id * (90000 / ifps);          // media_pipeline.py:291-292
-    j.hdr_w = s->dst_w; j.hdr_h = s->dst_h; j.timing = s->timing;
+    j.hdr_w = s->dst_w; j.hdr_h = s->dst_h;
+    // B2V_FLAG_TIMING_CSC samples: the event pair goes around the CSC launch of every 4th picture (two timing events per picture
+    // cost the step 5 %; a quarter of the launches of the timed region is plenty for a mean)
+    j.timing = s->timing && (!s->timing_csc_only || (s->frame_id & 3) == 0);
     s->frame_id++;
     fp.idr = idr;
     fp.rc_mode = s->cfg.rc_mode;
@@ -432,7 +435,7 @@ int submit_common(Session* s, const uint8_t* d_bgra, int stride, int in_slot, in
     s->stats.frames_submitted++;
   }
   CscParams cp = csc_params(s, d_bgra, stride, s->d_cur, tmap);
-  cudaEvent_t* ev = s->timing ? s->ev_t[out_idx] : nullptr;
+  cudaEvent_t* ev = j.timing ? s->ev_t[out_idx] : nullptr;
   if (ev && s->d_csc_ts && s->encode) {
     cp.ts = s->d_csc_ts + 2 * out_idx;
     cudaMemsetAsync(cp.ts, 0xFF, sizeof(unsigned long long), s->st_enc);
@@ -541,6 +544,7 @@ int b2v_create(const b2v_settings* cfg, b2v_cb cb, void* user, void** out) {
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   s->sm_count = prop.multiProcessorCount;
   cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking);
+  // (stream priorities — analysis high, entropy low — were tried and cost 4.5 %: 6520 vs 6830 pictures/s, three runs each)
   cudaStreamCreateWithFlags(&s->st_enc, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&s->st_pack, cudaStreamNonBlocking);

@@ -283,7 +283,7 @@ __device__ __forceinline__ void rc_step(const FrameCtx& f, int qp_used, long lon
 // ---- k_slice_scan: one block per slice.  Block-wide scans give every macroblock (a) its mb_skip_run and (b) the bit
 // offset of its first bit inside the slice RBSP.  Nothing is copied here, so a slice of many macroblock rows costs one
 // short loop iteration per 256 macroblocks.
-__global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
+__device__ __forceinline__ void slice_scan_body(const FrameCtx& f) {
   __shared__ long long s_warp_sum[SLICE_THREADS / 32];
   __shared__ int s_warp_max[SLICE_THREADS / 32];
   __shared__ long long s_carry_bits;
@@ -400,16 +400,17 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_scan(FrameCtx f) {
 constexpr int COPY_LANES = 8;
 constexpr int COPY_THREADS = 256;
 
-__global__ void __launch_bounds__(COPY_THREADS) k_slice_copy(FrameCtx f) {
-  const int gt = blockIdx.x * COPY_THREADS + threadIdx.x;
-  const int mb = gt / COPY_LANES, sub = gt % COPY_LANES;
-  if (mb >= f.mbw * f.mbh) return;
+__device__ __forceinline__ void slice_copy_body(const FrameCtx& f) {
+  const int s = blockIdx.x, sub = threadIdx.x % COPY_LANES;
+  const SliceGeo geo = slice_geo(f, s);
+  uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
+  for (int i = threadIdx.x / COPY_LANES; i < geo.n_mb; i += COPY_THREADS / COPY_LANES) {
+  const int mb = geo.mb0 + i;                                // the macroblocks of a slice are consecutive (whole rows, or a piece of one row)
   const uint32_t v = f.mb_nbits[mb];
-  if (v >> 31) return;                                       // P_Skip: folded into a later mb_skip_run
+  if (v >> 31) continue;                                     // P_Skip: folded into a later mb_skip_run
   const bool pcm = ((v >> 30) & 1u) != 0;
   const uint32_t nbits = v & 0x3fffffffu;
-  const int mby = mb / f.mbw, mbx = mb - mby * f.mbw, s = slice_of(f, mbx, mby);
-  uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
+  const int mby = mb / f.mbw, mbx = mb - mby * f.mbw;
   long long pos = f.mb_off[mb];
   if (!f.idr) {
     const uint32_t run = (uint32_t)f.mb_run[mb];
@@ -433,15 +434,16 @@ __global__ void __launch_bounds__(COPY_THREADS) k_slice_copy(FrameCtx f) {
       or_word(out, pp + 32LL * w, q);
     }
   }
+  }
 }
 
 // ---- k_slice_ep: one block per slice counts the emulation-prevention bytes the slice needs (7.4.1): a 03 goes in
 // front of byte i iff byte <= 3 and the run of zero bytes before it is even and >= 2.
-__global__ void __launch_bounds__(SLICE_THREADS) k_slice_ep(FrameCtx f) {
+__device__ __forceinline__ void slice_ep_body(const FrameCtx& f) {
   __shared__ int s_red[SLICE_THREADS / 32];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
-  const long long rbsp_bytes = f.slice_rbsp[s];
+  const long long rbsp_bytes = __ldcg(&f.slice_rbsp[s]);
   int ep = 0;
   for (long long w0 = (long long)tid * 4; w0 < rbsp_bytes; w0 += SLICE_THREADS * 4) {
     const uint32_t word = __ldcg(&out[w0 >> 2]);
@@ -466,6 +468,20 @@ __global__ void __launch_bounds__(SLICE_THREADS) k_slice_ep(FrameCtx f) {
     const int start_len = (geo.row0 % f.band_rows == 0 && geo.x0 == 0 && !f.idr) ? 4 : 3;     // 4-byte start code on the first NAL of (each band's) access unit
     f.slice_size[s] = (uint32_t)(start_len + 1 + rbsp_bytes + t);
   }
+}
+
+// ---- k_slice_build: the three per-slice stages in ONE launch (they only ever depended on each other inside a slice): scan ->
+// copy -> emulation-prevention count.  The block's own global writes (macroblock offsets, the RBSP words built with atomicOr) are
+// visible to it after a fence + barrier.
+static_assert(SLICE_THREADS == COPY_THREADS, "one block shape for the fused slice kernel");
+__global__ void __launch_bounds__(SLICE_THREADS) k_slice_build(FrameCtx f) {
+  slice_scan_body(f);
+  __threadfence();
+  __syncthreads();
+  slice_copy_body(f);
+  __threadfence();
+  __syncthreads();
+  slice_ep_body(f);
 }
 
 // ------------------------------------------------------------------------------------------------ k_pack_au
@@ -594,14 +610,12 @@ int launch_cavlc(const FrameCtx& f, cudaStream_t st) {
   return 1;
 }
 int launch_slice_scan(const FrameCtx& f, cudaStream_t st) {
-  k_slice_scan<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
+  k_slice_build<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);      // scan + copy + emulation-prevention count
   return 1;
 }
 int launch_slice_copy_ep(const FrameCtx& f, cudaStream_t st) {
-  const int mbs = f.mbw * f.mbh;
-  k_slice_copy<<<(mbs * COPY_LANES + COPY_THREADS - 1) / COPY_THREADS, COPY_THREADS, 0, st>>>(f);
-  k_slice_ep<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);
-  return 2;
+  (void)f; (void)st;          // folded into k_slice_build (launch_slice_scan)
+  return 0;
 }
 int launch_pack_cap(const FrameCtx& f, long long au_cap, cudaStream_t st) {
   k_pack_au<<<f.n_slices, PACK_THREADS, 0, st>>>(f, au_cap);

@@ -105,6 +105,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   const int r8 = lane >> 1, c8 = (lane & 1) * 8, rc4 = lane >> 2, cc4 = (lane & 3) * 4;
 
   // ---- stage the source block and the search window ------------------------------------------------
+  // one batch of independent global loads: source block, co-located reference block, and — speculatively, they are needed again a
+  // dependent-load latency later otherwise — the co-located chroma reference (the chroma prediction of a zero vector) and this
+  // macroblock's record of the previous picture (temporal predictor)
+  const uint32_t uv_coloc = __ldg(reinterpret_cast<const uint32_t*>(ref_uv + (size_t)(mby * 8 + rc4) * f.cw + x0 + cc4));
+  const MbInfo prev = f.mbinfo_prev[mb];                    // the previous picture's record (other half of the double buffer)
   {
     const uint2 v = *reinterpret_cast<const uint2*>(f.cur + (size_t)(y0 + r8) * f.cw + x0 + c8);
     *reinterpret_cast<uint2*>(&t.cur_y[r8][c8]) = v;
@@ -134,20 +139,24 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   }
   if (best == 0xffffffffu) {   // not static: stage the rest of the 48x48 search window
     const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
-    if (x_inside) {   // 512 more words = 16 per lane (of 18 slots): issue every load before the first shared-memory store
-      uint32_t v[18];
-      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref_y + x0 - 16);
+    if (x_inside) {   // 512 more words: lanes 0..23 take (row pair j, word) = two rows of 12 words per step — no index arithmetic
+      // beyond an add per step —, every load issued before the first shared-memory store
+      uint32_t v[24];
+      const int half = lane >= 12 ? 1 : 0, w = lane - 12 * half;
+      const bool mid = w >= 4 && w < 8;
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref_y + x0 - 16) + w;
+      if (lane < 24) {
 #pragma unroll
-      for (int k = 0; k < 18; k++) {
-        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        const bool centre = row >= 16 && row < 32 && w >= 4 && w < 8;
-        v[k] = centre ? 0u : __ldg(base + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * (f.cw >> 2) + w);
-      }
+        for (int j = 0; j < 24; j++) {
+          const int row = 2 * j + half;
+          const bool centre = j >= 8 && j < 16 && mid;
+          v[j] = centre ? 0u : __ldg(base + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * (f.cw >> 2));
+        }
 #pragma unroll
-      for (int k = 0; k < 18; k++) {
-        const int i = lane + 32 * k, row = i / WIN_WORDS, w = i - row * WIN_WORDS;
-        const bool centre = row >= 16 && row < 32 && w >= 4 && w < 8;
-        if (!centre) sm.win[row][w] = v[k];
+        for (int j = 0; j < 24; j++) {
+          const bool centre = j >= 8 && j < 16 && mid;
+          if (!centre) sm.win[2 * j + half][w] = v[j];
+        }
       }
     } else {   // picture edge: per-sample clamping (8.4.2.2.1 reference sample padding)
       for (int i = lane; i < WIN_ROWS * WIN_WORDS; i += 32) {
@@ -168,7 +177,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   // full-sample neighbours AND it costs less than the zero vector; quarter-sample refinement then runs as after a search. ----
   bool pred_hit = false, pred_frac = false;
   if (best == 0xffffffffu) {
-    const MbInfo prev = f.mbinfo_prev[mb];                  // the previous picture's record (other half of the double buffer)
     const int cdx = (prev.mvx + 2) >> 2, cdy = (prev.mvy + 2) >> 2;
     if (prev.type == MB_P16 && (cdx | cdy) != 0 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
       const uint32_t c0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), c1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
@@ -318,7 +326,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
     const int cwc = f.cw >> 1;
     const int ya = clip3i(ylo >> 1, yhi >> 1, mby * 8 + yi + rc4), yb = clip3i(ylo >> 1, yhi >> 1, mby * 8 + yi + rc4 + 1);
     uint32_t out = 0;
-    if ((xf | yf) == 0) {     // full-sample chroma position (static and most scrolling content): the (Cb,Cr) pairs are copied
+    if ((mvx | mvy) == 0) out = uv_coloc;      // zero vector: the co-located pairs, loaded with the first batch
+    else if ((xf | yf) == 0) {     // full-sample chroma position (most scrolling content): the (Cb,Cr) pairs are copied
 #pragma unroll
       for (int px = 0; px < 2; px++) {
         const int xa = clip3i(0, cwc - 1, mbx * 8 + xi + (lane & 3) * 2 + px);
