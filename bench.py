@@ -429,15 +429,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return [float(v) for v in t.tolist()]
 
+    from selkies_b200.multi_gpu import aggregate_throughput, gather_over_ranks as gather_ranks, session_device
+    assert world == 1 or session_device(rank, world) == local_rank       # one session per GPU, session i on GPU i mod n
+
     def gather_dict(d: dict):
-        """{key: [value on rank 0, rank 1, ...]} for a flat dict of floats"""
-        keys = sorted(d)
-        if world == 1:
-            return {k: [d[k]] for k in keys}
-        t = torch.zeros(world, len(keys), dtype=torch.float64, device="cuda")
-        t[rank] = torch.tensor([float(d[k]) for k in keys], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return {k: [float(v) for v in t[:, i].tolist()] for i, k in enumerate(keys)}
+        return gather_ranks(d, device="cuda")
 
     def sum_over_ranks(x: float) -> float:
         if world == 1:
@@ -494,10 +490,9 @@ def main():
     barrier()
     st = sess.stats()
     n_frames = args.steps * FRAMES_PER_STEP
-    t_ms = max_over_ranks(max(dev_ms, 0.0))
+    value, t_ms = aggregate_throughput(float(n_frames), max(dev_ms, 1e-6), device="cuda")      # sum of pictures / max time over ranks
     per_rank_ms = gather_over_ranks(max(dev_ms, 0.0))
     per_rank_wall_ms = gather_over_ranks(wall_ms)
-    value = sum_over_ranks(float(n_frames)) / (t_ms / 1000.0)
     host_resident = gather_dict(host_breakdown(st, None, n_frames))       # reset_stats ran right before the leg
 
     # ---------------- leg 1b: the same steps with the CSC event pairs on (roofline) ----------------------------------

@@ -26,3 +26,18 @@ def aggregate_throughput(units_this_rank: float, ms_this_rank: float, device=Non
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(u.item()) / (float(t.item()) / 1000.0), float(t.item())
+
+
+def gather_over_ranks(values: dict, device=None) -> dict:
+    """{key: [value on rank 0, rank 1, ...]} for a flat dict of numbers (same keys on every rank): the per-rank breakdown
+    bench.py prints next to the aggregate, so that a lagging rank names the wait that ate its time."""
+    import torch
+    import torch.distributed as dist
+    keys = sorted(values)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return {k: [float(values[k])] for k in keys}
+    world, rank = dist.get_world_size(), dist.get_rank()
+    t = torch.zeros(world, len(keys), dtype=torch.float64, device=device)
+    t[rank] = torch.tensor([float(values[k]) for k in keys], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return {k: [float(v) for v in t[:, i].tolist()] for i, k in enumerate(keys)}
