@@ -696,6 +696,34 @@ def main():
             py_surface = python_surface_leg(frames, local_rank)
         except Exception as e:
             py_surface = {"error": repr(e)}
+        try:      # how much of the GPU one free-running session leaves: two sessions on the same GPU, aggregate pictures/s
+            import threading as _th
+            res2 = [None, None]
+
+            def _one(i):
+                res2[i] = resident_leg(frames, 512, local_rank, warm=48, **cbr)
+            ts = [_th.Thread(target=_one, args=(i,)) for i in range(2)]
+            t0 = time.perf_counter()
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            content_legs = dict(content_legs or {})
+            content_legs["two_sessions_one_gpu_fps"] = sum(r["value"] for r in res2)
+            content_legs["two_sessions_note"] = ("two independent sessions of the headline workload on ONE GPU, each device-timed over 512 pictures, "
+                                                 "sum of the two rates (the headline `value` is one session per GPU, BASELINE configs[3])")
+        except Exception as e:
+            content_legs = dict(content_legs or {}, two_sessions_error=repr(e))
+        try:      # the headline content with a 64-picture scroll cycle instead of 16 (2.1 GB resident): the restart picture, in which
+            # nothing is predictable, is then 1 picture in 64
+            long_frames = synth_frames(64)
+            lc = resident_leg(long_frames, 512, local_rank, warm=64, **cbr)
+            content_legs = dict(content_legs or {})
+            content_legs["scroll_cycle64_fps"] = lc["value"]
+            content_legs["scroll_cycle64_bytes_per_picture"] = lc["bytes_per_picture"]
+            del long_frames
+        except Exception as e:
+            content_legs = dict(content_legs or {}, scroll_cycle64_error=repr(e))
 
     # ---------------- CPU baseline (rank 0, N=1 only; bounded sample) ------------------------------------------
     cpu = parity = None
