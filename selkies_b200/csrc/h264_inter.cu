@@ -137,8 +137,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
     sad0 = __reduce_add_sync(FULL, (int)s0);
     if (sad0 > ME_EARLY_SAD_PER_LAMBDA * lambda) best = 0xffffffffu;
   }
-  if (best == 0xffffffffu) {   // not static: stage the rest of the 48x48 search window
-    const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
+  // ---- not static: stage the reference.  A macroblock that carries a vector from the previous picture first gets only what the
+  // temporal-predictor test, the refinement around it and the final prediction can touch — 24 rows x 8 words around the predicted
+  // position instead of the 48 x 12 window; the rest follows only if the predictor is rejected and the search has to run.
+  const int cdx = (prev.mvx + 2) >> 2, cdy = (prev.mvy + 2) >> 2;
+  const bool try_pred = prev.type == MB_P16 && (cdx | cdy) != 0 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15;
+  const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
+  bool window_complete = false;
+  auto stage_window = [&]() {
     if (x_inside) {   // 512 more words: lanes 0..23 take (row pair j, word) = two rows of 12 words per step — no index arithmetic
       // beyond an add per step —, every load issued before the first shared-memory store
       uint32_t v[24];
@@ -169,7 +175,28 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
         sm.win[row][w] = v;
       }
     }
+    window_complete = true;
     __syncwarp();
+  };
+  if (best == 0xffffffffu) {
+    if (x_inside && try_pred) {
+      // rows [13+cdy, 36+cdy] and bytes [13+cdx, 34+cdx] of the window cover the 3x3 predictor test (rows 15+cdy..32+cdy), the 6-tap
+      // support of a refinement around it (-3..+18) and the prediction; clamped so that 24 rows x 8 words stay inside the window
+      const int ra = min(max(13 + cdy, 0), WIN_ROWS - 24), wa = min(max((13 + cdx) >> 2, 0), WIN_WORDS - 8);
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref_y + x0 - 16);
+      uint32_t v[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int idx = lane + 32 * k, row = ra + (idx >> 3), w = wa + (idx & 7);
+        v[k] = __ldg(base + (size_t)clip3i(ylo, yhi, y0 - 16 + row) * (f.cw >> 2) + w);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const int idx = lane + 32 * k;
+        sm.win[ra + (idx >> 3)][wa + (idx & 7)] = v[k];
+      }
+      __syncwarp();
+    } else stage_window();
   }
   // ---- temporal-predictor early termination (oracle/h264_ref.c encode_inter_mb): the vector this macroblock
   // had in the previous picture, rounded to full samples (scrolling / panning content repeats it).  Accepted without the
@@ -177,8 +204,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   // full-sample neighbours AND it costs less than the zero vector; quarter-sample refinement then runs as after a search. ----
   bool pred_hit = false, pred_frac = false;
   if (best == 0xffffffffu) {
-    const int cdx = (prev.mvx + 2) >> 2, cdy = (prev.mvy + 2) >> 2;
-    if (prev.type == MB_P16 && (cdx | cdy) != 0 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
+    if (try_pred) {
       const uint32_t c0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), c1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
       uint32_t kc = 0, kmin = 0xffffffffu;
 #pragma unroll
@@ -201,6 +227,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
     }
   }
   const bool searched = best == 0xffffffffu;
+  if (searched && !window_complete) stage_window();          // predictor rejected: the search needs the whole window
   if (searched) {
   // ---- exhaustive search ---------------------------------------------------------------------------
   uint32_t c[16][4];
