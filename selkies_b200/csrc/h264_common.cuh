@@ -259,10 +259,11 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
   const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
   const int qpc = chroma_qp_tab[qp];
   const QuantParams q = make_quant(is_chroma ? qpc : qp, INTRA16);
-  int lv[16], w[16], w_dc = 0, n = 0, bx = 0, by = 0, comp = 0;
+  int lv[16], w[16], res[16], w_dc = 0, n = 0, bx = 0, by = 0, comp = 0;
+  // residual of this lane's block.  The two shapes (luma: 4 consecutive bytes per row; chroma: every other byte of 8) differ only in
+  // how the 16 samples are picked out; everything from the transform on runs ONCE for the whole warp (lanes 24..31 carry zeros)
   if (is_luma) {
     bx = blk_x[lane] * 4; by = blk_y[lane] * 4;
-    int res[16];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       uint32_t c = *reinterpret_cast<const uint32_t*>(&t.cur_y[by + i][bx]);
@@ -270,29 +271,32 @@ __device__ __forceinline__ int transform_mb(MbTile& t, int lane, int qp, int16_t
 #pragma unroll
       for (int j = 0; j < 4; j++) res[4 * i + j] = (int)((c >> (8 * j)) & 255) - (int)((p >> (8 * j)) & 255);
     }
-    fwd4x4(res, w);
   } else if (is_chroma) {
     comp = (lane - 16) >> 2;
     int b = (lane - 16) & 3;
     bx = (b & 1) * 4; by = (b >> 1) * 4;
-    int res[16];
+    const int sh = 8 * comp;
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) res[4 * i + j] = (int)t.cur_uv[by + i][(bx + j) * 2 + comp] - (int)t.pred_uv[by + i][(bx + j) * 2 + comp];
-    fwd4x4(res, w);
+    for (int i = 0; i < 4; i++) {
+      const uint2 c = *reinterpret_cast<const uint2*>(&t.cur_uv[by + i][bx * 2]), p = *reinterpret_cast<const uint2*>(&t.pred_uv[by + i][bx * 2]);
+      res[4 * i + 0] = (int)((c.x >> sh) & 255) - (int)((p.x >> sh) & 255);
+      res[4 * i + 1] = (int)((c.x >> (sh + 16)) & 255) - (int)((p.x >> (sh + 16)) & 255);
+      res[4 * i + 2] = (int)((c.y >> sh) & 255) - (int)((p.y >> sh) & 255);
+      res[4 * i + 3] = (int)((c.y >> (sh + 16)) & 255) - (int)((p.y >> (sh + 16)) & 255);
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < 16; k++) { lv[k] = 0; w[k] = 0; }
+    for (int k = 0; k < 16; k++) { lv[k] = 0; res[k] = 0; }
   }
+  fwd4x4(res, w);
   // ---- inter macroblock in which NOTHING survives quantisation (the common case on a desktop: static regions, and scrolled
   // regions whose prediction repeats last picture's residual): decided from the transformed coefficients with three maxima per
   // block + the chroma DC Hadamard — no level is computed.  The result is exactly what the full path below would produce
   // (every level 0 -> reconstruction = prediction, nothing stored, cbp 0), so the oracle needs no counterpart. ----
   if (!INTRA16) {
-    bool z = true;
-    if (is_luma) z = block_quantises_to_zero<false>(w, q);
-    else if (is_chroma) z = block_quantises_to_zero<true>(w, q);
+    // AC positions for everybody; the DC position counts for luma only (chroma DC goes through the 2x2 Hadamard below)
+    bool z = block_quantises_to_zero<true>(w, q);
+    if (is_luma) z = z && abs(w[0]) * q.mf[0] < (1 << q.qbits) - q.f;
     {
       const int b = (lane - 16) & 3, d = is_chroma ? w[0] : 0;
       const int o1 = __shfl_xor_sync(FULL, d, 1), o2 = __shfl_xor_sync(FULL, d, 2), o3 = __shfl_xor_sync(FULL, d, 3);
