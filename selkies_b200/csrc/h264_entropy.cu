@@ -85,25 +85,28 @@ __global__ void __launch_bounds__(32 * CAVLC_WARPS) k_cavlc_mb(FrameCtx f) {
   const int mbx = mb % f.mbw, mby = mb / f.mbw;
   const MbInfo mi = f.mbinfo[mb];
   uint32_t* words = s_words[warp];
-#pragma unroll
-  for (int i = lane; i < MB_WORDS; i += 32) words[i] = 0;
 
   // ---- macroblock header fields ---------------------------------------------------------------------
+  // (most macroblocks of a desktop picture leave through the P_Skip exit: nothing that only a coded macroblock needs — the bit
+  // scratch, the mvd — is touched before it)
   const int cbp_l = mi.cbp & 15, cbp_c = mi.cbp >> 4;
-  bool skip = false;
   int mvdx = 0, mvdy = 0;
   if (!f.idr) {
     const MvCtx mc = mv_ctx(f, mbx, mby);
-    int sx, sy, px, py;
-    mv_pred_skip(mc, sx, sy);
-    skip = mi.type == MB_P16 && mi.cbp == 0 && mi.mvx == sx && mi.mvy == sy;
+    if (mi.type == MB_P16 && mi.cbp == 0) {
+      int sx, sy;
+      mv_pred_skip(mc, sx, sy);
+      if (mi.mvx == sx && mi.mvy == sy) {        // P_Skip: no bits; the slice scan folds it into mb_skip_run
+        if (lane == 0) f.mb_nbits[mb] = 0x80000000u;
+        return;
+      }
+    }
+    int px, py;
     mv_pred16(mc, px, py);
     mvdx = mi.mvx - px; mvdy = mi.mvy - py;
   }
-  if (skip) {                                    // P_Skip: no bits; k_slice_bits folds it into mb_skip_run
-    if (lane == 0) f.mb_nbits[mb] = 0x80000000u;
-    return;
-  }
+#pragma unroll
+  for (int i = lane; i < MB_WORDS; i += 32) words[i] = 0;
   if (mi.type == MB_PCM) {                       // I_PCM: only mb_type here; alignment + 384 raw samples are placed by k_slice_bits
     if (lane == 0) {
       const uint32_t code = f.idr ? 25u : 30u;

@@ -341,12 +341,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   // ---- prediction ------------------------------------------------------------------------------------
   {
     if (!refine) {
-      const uint8_t* wb = reinterpret_cast<const uint8_t*>(&sm.win[dyi + r8][0]) + dxi + c8;
-      uint32_t p0 = 0, p1 = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) { p0 |= (uint32_t)wb[j] << (8 * j); p1 |= (uint32_t)wb[4 + j] << (8 * j); }
-      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = p0;
-      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = p1;
+      const int bo = dxi + c8;                                              // 8 samples at byte offset bo of window row dyi + r8
+      const uint32_t* wr = &sm.win[dyi + r8][bo >> 2];
+      const int sh = (bo & 3) * 8;
+      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8]) = __funnelshift_r(wr[0], wr[1], sh);
+      *reinterpret_cast<uint32_t*>(&t.pred_y[r8][c8 + 4]) = __funnelshift_r(wr[1], wr[2], sh);
     }
     // chroma: mvC = luma mv, in 1/8 chroma samples (8.4.1.4, 8.4.2.2.2)
     const int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
