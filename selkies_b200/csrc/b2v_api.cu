@@ -62,14 +62,17 @@ inline int64_t now_ns() {
 // busy pipeline completes within tens of microseconds); after that the thread sleeps in ~25 us steps, so an idle-ish session
 // costs a few thousand wake-ups per second instead of a spinning core.  (Round 1 slept in the driver on blocking-sync events:
 // on one node of the pool one GPU's wake-ups took ~3 ms each, 20x the picture time — VERDICT r1 "What's weak" #2.)
-constexpr int64_t kSpinNs = 30000, kSleepNs = 25000;
+constexpr int64_t kSpinNs = 30000, kSleepNs = 25000, kGiveUpNs = 30LL * 1000000000LL;
 inline cudaError_t wait_event_polling(cudaEvent_t ev, bool* slept) {
   const int64_t t0 = now_ns();
   for (;;) {
     const cudaError_t e = cudaEventQuery(ev);
     if (e != cudaErrorNotReady) return e;
-    if (now_ns() - t0 < kSpinNs) {
+    const int64_t waited = now_ns() - t0;
+    if (waited < kSpinNs) {
       for (int i = 0; i < 16; i++) __builtin_ia32_pause();
+    } else if (waited > kGiveUpNs) {
+      return cudaErrorLaunchTimeout;      // a picture takes well under 10 ms: 30 s means a wedged device — fail the session loudly instead of hanging
     } else {
       *slept = true;
       timespec ts{0, (long)kSleepNs};

@@ -317,3 +317,25 @@ def test_idr_subrow_slices_striped_bit_exact():
                 assert got[k].data == au[off: off + size], (i, b)
                 k += 1
     assert k == len(got)
+
+
+@pytest.mark.parametrize("name,kbps", [("desktop_scroll", 8000), ("gradient_pan", 8000), ("gradient_pan", 20000)])
+def test_cbr_holds_its_target_1080p(name, kbps):
+    """CBR must be CBR.  1080p60, 180 pictures: the second half within +-10 % of the target, no one-second window after
+    the first second above +20 % (knob range: settings.py:49)."""
+    w, h, fps, n = 1920, 1080, 60.0, 180
+    gen = synth.desktop if name == "desktop_scroll" else synth.gradient
+    with Session(w, h, rc_mode=N.B2V_RC_CBR, bitrate_kbps=kbps, fps=fps, collect=True) as s:
+        for t in range(n):
+            s.submit(gen(w, h, t))
+        s.flush()
+        got = s.take_frames()
+    sizes = np.array([len(g.data) for g in got], float)
+    tb = kbps * 1000.0 / fps / 8.0
+    steady = sizes[n // 2:].mean() / tb
+    win = int(fps)
+    worst = max(sizes[i:i + win].sum() / (tb * win) for i in range(win, n - win + 1))
+    qps = [g.qp for g in got[n // 2:]]
+    assert 10 < min(qps) and max(qps) < 51, qps              # the controller is not sitting at a limit on these runs
+    assert 0.9 <= steady <= 1.1, (steady, qps[-10:])
+    assert worst <= 1.2, worst
