@@ -196,7 +196,12 @@ class ScreenCapture:
             if not callable(callback):
                 raise TypeError("callback must be callable or a StripeCallback")
             if not jpeg and bool(getattr(settings, "h264_fullcolor", False)):
-                raise ValueError("h264_fullcolor (4:4:4) is not implemented; the pipeline encodes 4:2:0")
+                # The client picks a SUPERSET decoder configuration for this switch (avc1.F400xx, High 4:4:4 Predictive;
+                # selkies-ws-core.js:475-496), under which a Constrained-Baseline 4:2:0 stream decodes as well: the stream stays
+                # 4:2:0 (chroma at half resolution) instead of the capture failing.
+                import warnings
+                warnings.warn("h264_fullcolor: the B200 pipeline encodes 4:2:0 (Constrained Baseline); the stream decodes under the 4:4:4 decoder "
+                              "configuration the client selects, with chroma at half resolution", RuntimeWarning, stacklevel=2)
             w, h = int(settings.capture_width), int(settings.capture_height)
             w -= w & 1
             h -= h & 1                                # the reference forces even sizes (webrtc_mode.py:397-402)

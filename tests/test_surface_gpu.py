@@ -55,10 +55,12 @@ def test_screen_capture_contract_and_parity():
         assert got[i][1] == ref                                  # same bytes as the oracle behind the plugin API
         hdr = got[i][2][:10]
         assert hdr[0] == 0x04 and hdr[1] == (1 if i == 0 else 0) and int.from_bytes(hdr[2:4], "big") == i
-    with pytest.raises(ValueError):
-        bad = CaptureSettings()
-        bad.h264_fullcolor = True                                # 4:4:4 is the one CaptureSettings switch this pipeline refuses
-        ScreenCapture().start_capture(bad, cb)
+    with pytest.warns(RuntimeWarning):                           # h264_fullcolor: accepted, the stream stays 4:2:0 (superset decoder config)
+        fc = CaptureSettings()
+        fc.capture_width, fc.capture_height, fc.h264_fullcolor = 64, 48, True
+        cap2 = ScreenCapture(ArraySource([synth.noise(64, 48, 1)], loop=False))
+        cap2.start_capture(fc, lambda p, u: None)
+        cap2.stop_capture()
 
 
 def test_media_pipeline_b200_end_to_end():
