@@ -91,6 +91,8 @@ typedef struct {
   int8_t  i16_mode, chroma_mode;
   uint8_t cbp;            /* luma bits 0..3, chroma << 4 */
   int16_t mv[2];          /* quarter-sample units */
+  int8_t  me_bad;         /* motion estimation searched exhaustively and found nothing better than a mean absolute difference of 32: new content */
+  int16_t me_mv[2];       /* what motion estimation chose for this picture (== mv unless the macroblock then became I_PCM); read by the anchor predictor */
   int8_t  i4_modes[16];   /* Intra4x4PredMode per 4x4 block, raster y*4+x (type 3 only) */
 } mb_t;
 
@@ -118,7 +120,7 @@ typedef struct {
   int stripe_fn[MAX_STRIPES];
   int32_t stripe_tab[MAX_STRIPES][3];   /* last picture: byte offset, size, coded flag */
   uint8_t sps_band[2][64]; int sps_band_len[2];   /* [0] regular band, [1] last band (may be shorter / cropped) */
-  int no_i4, no_tpred, no_refine_cap;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED / B2V_REF_NO_REFINE_CAP, read once at create) */
+  int no_i4, no_tpred, no_refine_cap, no_anchor, no_newcontent;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED / B2V_REF_NO_REFINE_CAP, read once at create) */
 } enc_t;
 
 static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -607,6 +609,7 @@ static void encode_intra_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
 /* ------------------------------------------------------------------ inter macroblock (8.4) */
 #define ME_EARLY_SAD_PER_LAMBDA 96
 #define ME_REFINE_MAX_SAD 8192             /* no sub-sample refinement of a full-sample match this bad */
+#define ME_NEWCONTENT_DY 2                 /* vertical range of the reduced search on new content */
 #define ME_PRED_SAD_FACTOR 4
 #define ME_FRAC_PENALTY_BITS 4   /* fractional vectors pay 4 extra bits: they cost more mvd bits than the zero-relative estimate sees */
 static int se_bits(int v) { unsigned c = v > 0 ? 2u * v - 1 : (unsigned)(-2 * v); int len = 0; c += 1; while ((c >> len) > 1) len++; return 2 * len + 1; }
@@ -651,6 +654,37 @@ static void band_rows(const enc_t* e, int mby, int* r0, int* r1) {
   *r1 = *r0 + e->stripe_rows; if (*r1 > e->mbh) *r1 = e->mbh;
 }
 
+/* Anchor macroblocks: one per 4x4 group of macroblocks (rows counted from the band's first row), at offset (1,1) of its group
+ * (clamped into the band / picture).  The anchors of a P picture are analysed first; when the temporal predictor of any other
+ * macroblock fails, the vector its group's anchor has just found is tried before the exhaustive search — coherent motion that
+ * STARTS in this picture (a scroll or pan after a still or a cut, where last picture's vectors are useless) is then searched for
+ * once per sixteen macroblocks instead of once per macroblock. */
+static void anchor_of(const enc_t* e, int mbx, int mby, int* ax, int* ay) {
+  int br0, br1; band_rows(e, mby, &br0, &br1);
+  *ax = 4 * (mbx / 4) + 1; if (*ax > e->mbw - 1) *ax = e->mbw - 1;
+  *ay = br0 + 4 * ((mby - br0) / 4) + 1; if (*ay > br1 - 1) *ay = br1 - 1;
+}
+static int is_anchor(const enc_t* e, int mbx, int mby) { int ax, ay; anchor_of(e, mbx, mby, &ax, &ay); return ax == mbx && ay == mby; }
+
+/* candidate (cdx,cdy), full-sample: accepted when its SAD is within 4x the noise threshold AND it is a strict local minimum of the
+ * cost over its 8 full-sample neighbours AND it costs less than the zero vector; *key = its search key */
+static int try_candidate(const uint8_t cy[256], uint8_t win[48][48], int cdx, int cdy, int lambda, int sad0, uint32_t* key) {
+  if (!(cdx || cdy) || cdx < -15 || cdx > 14 || cdy < -15 || cdy > 15) return 0;
+  uint32_t kc = 0, kmin = 0xffffffffu;
+  for (int j = -1; j <= 1; j++)
+    for (int i = -1; i <= 1; i++) {
+      int sad = 0;
+      for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) sad += iabs(cy[r * 16 + c] - win[16 + cdy + j + r][16 + cdx + i + c]);
+      const uint32_t cost = (uint32_t)(sad + lambda * (se_bits(4 * (cdx + i)) + se_bits(4 * (cdy + j))));
+      const uint32_t k = (cost << 11) | (uint32_t)((cdy + j + 16) * 32 + (cdx + i + 16));
+      if (i == 0 && j == 0) kc = k; else if (k < kmin) kmin = k;
+    }
+  const int sadc = (int)(kc >> 11) - lambda * (se_bits(4 * cdx) + se_bits(4 * cdy));
+  const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (16 * 32 + 16);     /* ... and it must beat the zero vector */
+  if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { *key = kc; return 1; }
+  return 0;
+}
+
 static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby, int qp) {
   mb_t* m = &e->mbs[mby * e->mbw + mbx];
   const int prev_type = m->type, prev_mvx = m->mv[0], prev_mvy = m->mv[1];   /* this macroblock in the previous picture */
@@ -680,25 +714,23 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
    * threshold AND it is a strict local minimum of the cost over its 8 full-sample neighbours (all inside the search range)
    * AND it costs less than the zero vector (otherwise a stale vector could survive on a scene that has become static);
    * quarter-sample refinement then runs as after a search. */
-  int pred_hit = 0;
+  int pred_hit = 0, src_mvx = 0, src_mvy = 0, dyr = 16;      /* src_mv: the vector the accepted candidate was derived from */
   if (search && prev_type == 1 && !e->no_tpred) {
     const int cdx = asr(prev_mvx + 2, 2), cdy = asr(prev_mvy + 2, 2);
-    if ((cdx || cdy) && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15) {
-      uint32_t kc = 0, kmin = 0xffffffffu;
-      for (int j = -1; j <= 1; j++)
-        for (int i = -1; i <= 1; i++) {
-          int sad = 0;
-          for (int r = 0; r < 16; r++) for (int c = 0; c < 16; c++) sad += iabs(cy[r * 16 + c] - win[16 + cdy + j + r][16 + cdx + i + c]);
-          const uint32_t cost = (uint32_t)(sad + lambda * (se_bits(4 * (cdx + i)) + se_bits(4 * (cdy + j))));
-          const uint32_t key = (cost << 11) | (uint32_t)((cdy + j + 16) * 32 + (cdx + i + 16));
-          if (i == 0 && j == 0) kc = key; else if (key < kmin) kmin = key;
-        }
-      const int sadc = (int)(kc >> 11) - lambda * (se_bits(4 * cdx) + se_bits(4 * cdy));
-      const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (16 * 32 + 16);     /* ... and it must beat the zero vector */
-      if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; best = kc; }
-    }
+    if (try_candidate(cy, win, cdx, cdy, lambda, sad0, &best)) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; src_mvx = prev_mvx; src_mvy = prev_mvy; }
   }
-  for (int dy = -16; search && dy <= 16; dy++)
+  /* anchor predictor: the vector the anchor of this macroblock's 4x4 group found in THIS picture (anchors run first) */
+  if (search && !e->no_tpred && !e->no_anchor && !is_anchor(e, mbx, mby)) {
+    int ax, ay; anchor_of(e, mbx, mby, &ax, &ay);
+    const mb_t* a = &e->mbs[ay * e->mbw + ax];
+    const int cdx = asr(a->me_mv[0] + 2, 2), cdy = asr(a->me_mv[1] + 2, 2);
+    if (try_candidate(cy, win, cdx, cdy, lambda, sad0, &best)) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; src_mvx = a->me_mv[0]; src_mvy = a->me_mv[1]; }
+    /* new content: the anchor's exhaustive search found no match worth the name and this macroblock's co-located block is as far
+     * off — another 1089-candidate search would only pick the least bad of the noise.  The search shrinks to the five rows
+     * around dy = 0 (160 candidates: most of what picking a minimum among noise buys, for a sixth of the work). */
+    else if (a->me_bad && sad0 >= ME_REFINE_MAX_SAD && !e->no_newcontent) dyr = ME_NEWCONTENT_DY;
+  }
+  for (int dy = -dyr; search && dy <= dyr; dy++)
     for (int dx = -16; dx <= 15; dx++) {
       int sad = 0;
       for (int r = 0; r < 16; r++) {
@@ -721,8 +753,9 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   uint8_t Gp[22][22], bq[18][17], hq[17][18], jq[17][17];   /* Gp[v+3][u+3], bq[v+1][u+1], hq[v+1][u+1], jq[v+1][u+1] */
   /* not worth refining when the full-sample match is already within the quantisation noise of this QP */
   const int sad_int = (int)(best >> 11) - lambda * (se_bits(4 * bdx) + se_bits(4 * bdy));
+  m->me_bad = search && sad_int >= ME_REFINE_MAX_SAD;
   /* a predictor hit whose previous vector was full-sample is not refined again: the previous refinement already preferred it */
-  const int pred_frac = pred_hit && ((prev_mvx | prev_mvy) & 3);
+  const int pred_frac = pred_hit && ((src_mvx | src_mvy) & 3);
   /* ... nor when it is hopeless (mean absolute difference of 32 per sample and more: new content, nothing to polish) */
   if ((search || pred_frac) && iabs(bdx) <= 13 && iabs(bdy) <= 13 && sad_int > ME_EARLY_SAD_PER_LAMBDA * lambda && (e->no_refine_cap || sad_int < ME_REFINE_MAX_SAD)) {
     int16_t b1[22][17];
@@ -757,7 +790,7 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
     luma_mc_planes(Gp, bq, hq, jq, cx, cyq, py);
 #undef GW
   }
-  m->mv[0] = (int16_t)mvx; m->mv[1] = (int16_t)mvy;
+  m->mv[0] = m->me_mv[0] = (int16_t)mvx; m->mv[1] = m->me_mv[1] = (int16_t)mvy;
   /* prediction: luma from the planes above, or a full-sample copy; chroma bilinear 1/8 (8.4.2.2.2) */
   if (!have_planes)
     for (int r = 0; r < 16; r++)
@@ -1151,7 +1184,7 @@ void* b2v_ref_enc_create(int width, int height, int slice_rows) {
   e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
   e->fb[0].qp = e->fb[1].qp = -1; e->paint_burst = 1;
   e->seg_cols = e->slice_rows == 1 ? auto_seg_cols(e->mbw, e->mbh) : 0;
-  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL; e->no_refine_cap = getenv("B2V_REF_NO_REFINE_CAP") != NULL;
+  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL; e->no_refine_cap = getenv("B2V_REF_NO_REFINE_CAP") != NULL; e->no_anchor = getenv("B2V_REF_NO_ANCHOR") != NULL; e->no_newcontent = getenv("B2V_REF_NO_NEWCONTENT") != NULL;
   write_param_sets(e);
   return e;
 }
@@ -1220,9 +1253,12 @@ int64_t b2v_ref_enc_encode(void* h, const uint8_t* cur_nv12, int idr, int rc_mod
         for (int mbx = x0; mbx < x1; mbx++) encode_intra_mb(e, cur_nv12, mbx, mby, qp);
     }
   } else {
+    /* anchors first (their vectors are candidates for the rest of their groups), then everybody else */
+    for (int pass = 0; pass < 2; pass++) {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int mby = 0; mby < e->mbh; mby++)
-      for (int mbx = 0; mbx < e->mbw; mbx++) encode_inter_mb(e, cur_nv12, mbx, mby, qp);
+      for (int mby = 0; mby < e->mbh; mby++)
+        for (int mbx = 0; mbx < e->mbw; mbx++) if (is_anchor(e, mbx, mby) == (pass == 0)) encode_inter_mb(e, cur_nv12, mbx, mby, qp);
+    }
   }
   /* phase B: entropy coding per slice, then concatenation */
   uint8_t* skip = (uint8_t*)calloc(mbs, 1);

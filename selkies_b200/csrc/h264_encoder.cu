@@ -30,6 +30,7 @@ struct Encoder {
   int16_t* coef[2] = {nullptr, nullptr};
   uint8_t* nnz[2] = {nullptr, nullptr};
   long long* mb_off = nullptr; int* mb_run = nullptr;
+  unsigned long long* me_pub = nullptr;   // anchor macroblocks' vectors of the picture being analysed (h264_inter.cu)
   uint32_t *mb_words = nullptr, *mb_nbits = nullptr, *slice_buf = nullptr, *slice_size = nullptr, *slice_rbsp = nullptr;
   long long* slice_bits = nullptr;
   int slice_words = 0;
@@ -150,6 +151,8 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
     ECK(cudaMalloc((void**)&e->nnz[b], mbs * 32));
     ECK(cudaMemset(e->nnz[b], 0, mbs * 32));
   }
+  ECK(cudaMalloc((void**)&e->me_pub, mbs * sizeof(unsigned long long)));
+  ECK(cudaMemset(e->me_pub, 0, mbs * sizeof(unsigned long long)));
   ECK(cudaMalloc((void**)&e->mb_words, mbs * MB_WORDS * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->mb_nbits, mbs * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->mb_off, mbs * sizeof(long long)));
@@ -210,7 +213,7 @@ void encoder_destroy(Encoder* e) {
   if (!e) return;
   void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo[0], e->mbinfo[1], e->coef[0], e->coef[1], e->nnz[0], e->nnz[1], e->mb_words, e->mb_nbits, e->slice_buf,
                   e->slice_size, e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes[0],
-                  e->i4modes[1], e->band_fn, e->band_coded};
+                  e->i4modes[1], e->band_fn, e->band_coded, e->me_pub};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) {
     if (e->ev_analysed[b]) cudaEventDestroy(e->ev_analysed[b]);
@@ -237,6 +240,11 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   f.frame_num = e->frame_num; f.idr_pic_id = e->idr_count; f.pic = (int)(e->pic & 0x7fffffff);
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
   f.mbinfo = e->mbinfo[par]; f.mbinfo_prev = e->mbinfo[par ^ 1]; f.i4modes = e->i4modes[par]; f.coef = e->coef[par]; f.nnz = e->nnz[par];
+  f.me_pub = e->me_pub;
+  {   // anchors: ceil(mbw/4) columns x (groups of 4 rows inside every band)
+    const int rows_last = e->mbh - (e->n_bands - 1) * e->band_rows;
+    f.n_anchor = ((e->mbw + 3) / 4) * ((e->n_bands - 1) * ((e->band_rows + 3) / 4) + (rows_last + 3) / 4);
+  }
   f.mb_words = e->mb_words; f.mb_nbits = e->mb_nbits; f.mb_off = e->mb_off; f.mb_run = e->mb_run;
   f.slice_buf = e->slice_buf; f.slice_words = seg ? e->seg_slice_words : e->slice_words; f.slice_size = e->slice_size; f.slice_rbsp = e->slice_rbsp;
   f.slice_bits = e->slice_bits; f.paint_trigger = p->paint_trigger; f.paint_qp = p->paint_qp; f.paint_burst = p->paint_burst; f.progress = e->progress; f.rc = e->rc;

@@ -37,6 +37,7 @@ struct alignas(16) InterSm {      // one per warp; the 16-byte size padding keep
 constexpr int ME_PRED_SAD_FACTOR = 4;      // temporal predictor accepted up to 4x the early-termination threshold (and only as a strict local minimum)
 constexpr int ME_FRAC_PENALTY_BITS = 4;   // fractional vectors pay 4 extra bits in the refinement cost
 constexpr int ME_REFINE_MAX_SAD = 8192;   // no sub-sample refinement of a full-sample match this bad
+constexpr int ME_NEWCONTENT_DY = 2;       // vertical range of the reduced search on new content
 
 // Table 8-12 as data: every fractional position is one plane sample or the rounded average of two.
 // entry = p1 | dx1<<2 | dy1<<3 | p2<<4 | dx2<<7 | dy2<<8, planes 0 G (full sample), 1 b, 2 h, 3 j, p2 = 4: none
@@ -88,17 +89,80 @@ __host__ __device__ constexpr int se_bits_c(int v) {
   return 2 * len + 1;
 }
 
+// Full-sample search over dx in [-16,15] (one candidate column per lane) and dy in [-DYR,DYR]: every window row is byte-aligned once
+// per lane with funnel shifts and feeds the (row, dy) pairs it belongs to; 2*DYR+1 SAD accumulators live in registers.  Returns the
+// warp-wide minimum of cost << 11 | candidate index.  DYR = 16 is the exhaustive search, a small DYR the reduced one for new content.
+template <int DYR>
+__device__ __forceinline__ uint32_t search_rows(const InterSm& sm, int lane, int lambda) {
+  const MbTile& t = sm.t;
+  uint32_t c[16][4];
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    const uint4 v = *reinterpret_cast<const uint4*>(&t.cur_y[r][0]);
+    c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
+  }
+  constexpr int N = 2 * DYR + 1, Y0 = 16 - DYR;
+  uint32_t acc[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) acc[i] = 0;
+  const int wi = lane >> 2, sh = (lane & 3) * 8;
+#pragma unroll
+  for (int y = Y0; y < Y0 + N + 15; y++) {
+    const uint32_t* wr = sm.win[y] + wi;
+    const uint32_t w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3], w4 = wr[4];
+    const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      const int k = y - r - Y0;
+      if (k >= 0 && k < N)
+        acc[k] = sad4acc(c[r][0], a0, sad4acc(c[r][1], a1, sad4acc(c[r][2], a2, sad4acc(c[r][3], a3, acc[k]))));
+    }
+  }
+  const int bits_x = se_bits_c(4 * (lane - 16));
+  uint32_t best = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const int dyi = k + Y0;                     // dy + 16
+    const uint32_t cost = acc[k] + (uint32_t)(lambda * (bits_x + se_bits_c(4 * (dyi - 16))));
+    best = min(best, (cost << 11) | (uint32_t)(dyi * 32 + lane));
+  }
+  return __reduce_min_sync(FULL, best);
+}
+
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f) {
   __shared__ __align__(16) InterSm sm_all[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mb = blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (mb >= f.mbw * f.mbh) return;
+  // Warp -> macroblock.  The first n_anchor warps of the grid take the ANCHOR macroblocks (one per 4x4 group of macroblocks, at
+  // offset (1,1) of its group, groups counted inside each band; oracle/h264_ref.c anchor_of()), the rest walk the picture in raster
+  // order and leave the anchors out.  An anchor publishes its vector as soon as motion estimation is done; the other macroblocks
+  // of its group try that vector before they fall back to the exhaustive search (below).  Anchors never wait for anybody and sit
+  // in the lowest-numbered blocks, so a waiting warp always waits for a block that is already running or finished.
+  const int gw = blockIdx.x * WARPS_PER_BLOCK + warp;
+  const int gcols = (f.mbw + 3) >> 2;
+  int mbx, mby, band_r0, ax, ay;
+  bool anchor;
+  if (gw < f.n_anchor) {
+    const int gr = gw / gcols, gc = gw - gr * gcols, grows_band = (f.band_rows + 3) >> 2;
+    const int band = min(gr / grows_band, f.n_bands - 1);
+    band_r0 = band * f.band_rows;
+    mbx = min(4 * gc + 1, f.mbw - 1);
+    mby = band_r0 + min(4 * (gr - band * grows_band) + 1, min(f.mbh - band_r0, f.band_rows) - 1);
+    ax = mbx; ay = mby; anchor = true;
+  } else {
+    const int m = gw - f.n_anchor;
+    if (m >= f.mbw * f.mbh) return;
+    mby = m / f.mbw; mbx = m - mby * f.mbw;
+    band_r0 = mby / f.band_rows * f.band_rows;
+    ax = min(4 * (mbx >> 2) + 1, f.mbw - 1);
+    ay = band_r0 + min(4 * ((mby - band_r0) >> 2) + 1, min(f.mbh - band_r0, f.band_rows) - 1);
+    if (ax == mbx && ay == mby) return;            // an anchor: one of the first warps has it
+    anchor = false;
+  }
+  const int mb = mby * f.mbw + mbx, x0 = mbx * 16, y0 = mby * 16;
   InterSm& sm = sm_all[warp];
   MbTile& t = sm.t;
-  const int mbx = mb % f.mbw, mby = mb / f.mbw, x0 = mbx * 16, y0 = mby * 16;
   const int qp = frame_qp(f);
   // reference rows this macroblock may touch: its own band (the band's decoder pads at the band's edges, 8.4.2.2.1)
-  const int band_r0 = mby / f.band_rows * f.band_rows;
   const int ylo = band_r0 * 16, yhi = min(f.mbh, band_r0 + f.band_rows) * 16 - 1;
   const size_t ysz = (size_t)f.cw * f.ch;
   const uint8_t* __restrict__ ref_y = f.ref; const uint8_t* __restrict__ ref_uv = f.ref + ysz;
@@ -202,65 +266,49 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   // had in the previous picture, rounded to full samples (scrolling / panning content repeats it).  Accepted without the
   // exhaustive search when its SAD is within 4x the noise threshold AND it is a strict local minimum of the cost over its 8
   // full-sample neighbours AND it costs less than the zero vector; quarter-sample refinement then runs as after a search. ----
-  bool pred_hit = false, pred_frac = false;
-  if (best == 0xffffffffu) {
-    if (try_pred) {
-      const uint32_t c0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), c1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
-      uint32_t kc = 0, kmin = 0xffffffffu;
+  bool pred_hit = false, pred_frac = false, reduced = false;
+  // candidate (kx,ky), full samples, window staged around it: true (and `best` = its key) when it passes the three conditions
+  auto test_candidate = [&](int kx, int ky) -> bool {
+    const uint32_t c0 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8]), c1 = *reinterpret_cast<const uint32_t*>(&t.cur_y[r8][c8 + 4]);
+    uint32_t kc = 0, kmin = 0xffffffffu;
 #pragma unroll
-      for (int j = -1; j <= 1; j++) {
+    for (int j = -1; j <= 1; j++) {
 #pragma unroll
-        for (int i = -1; i <= 1; i++) {
-          const int bx = 16 + cdx + i + c8;
-          const uint32_t* wr = &sm.win[16 + cdy + j + r8][bx >> 2];
-          const int sh = (bx & 3) * 8;
-          const uint32_t a0 = __funnelshift_r(wr[0], wr[1], sh), a1 = __funnelshift_r(wr[1], wr[2], sh);
-          const int sad = __reduce_add_sync(FULL, (int)sad4acc(c0, a0, sad4acc(c1, a1, 0u)));
-          const uint32_t cost = (uint32_t)(sad + lambda * (se_bits_dev(4 * (cdx + i)) + se_bits_dev(4 * (cdy + j))));
-          const uint32_t key = (cost << 11) | (uint32_t)((cdy + j + 16) * 32 + (cdx + i + 16));
-          if (i == 0 && j == 0) kc = key; else kmin = min(kmin, key);
-        }
+      for (int i = -1; i <= 1; i++) {
+        const int bx = 16 + kx + i + c8;
+        const uint32_t* wr = &sm.win[16 + ky + j + r8][bx >> 2];
+        const int sh = (bx & 3) * 8;
+        const uint32_t a0 = __funnelshift_r(wr[0], wr[1], sh), a1 = __funnelshift_r(wr[1], wr[2], sh);
+        const int sad = __reduce_add_sync(FULL, (int)sad4acc(c0, a0, sad4acc(c1, a1, 0u)));
+        const uint32_t cost = (uint32_t)(sad + lambda * (se_bits_dev(4 * (kx + i)) + se_bits_dev(4 * (ky + j))));
+        const uint32_t key = (cost << 11) | (uint32_t)((ky + j + 16) * 32 + (kx + i + 16));
+        if (i == 0 && j == 0) kc = key; else kmin = min(kmin, key);
       }
-      const int sadc = (int)(kc >> 11) - lambda * (se_bits_dev(4 * cdx) + se_bits_dev(4 * cdy));
-      const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (uint32_t)(16 * 32 + 16);   // ... and it must beat the zero vector
-      if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { best = kc; pred_hit = true; pred_frac = ((prev.mvx | prev.mvy) & 3) != 0; }
     }
+    const int sadc = (int)(kc >> 11) - lambda * (se_bits_dev(4 * kx) + se_bits_dev(4 * ky));
+    const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (uint32_t)(16 * 32 + 16);   // ... and it must beat the zero vector
+    if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { best = kc; return true; }
+    return false;
+  };
+  if (best == 0xffffffffu && try_pred && test_candidate(cdx, cdy)) { pred_hit = true; pred_frac = ((prev.mvx | prev.mvy) & 3) != 0; }
+  // ---- anchor predictor (oracle/h264_ref.c encode_inter_mb): the temporal predictor failed (or there was none) — motion that
+  // STARTS in this picture.  Instead of one exhaustive search per macroblock, try what this group's anchor has just found. ----
+  if (best == 0xffffffffu && !anchor) {
+    if (!window_complete) stage_window();       // overlaps the wait; needed by the search anyway if the candidate is rejected
+    const volatile unsigned long long* pub = f.me_pub + (size_t)ay * f.mbw + ax;
+    unsigned long long v = 0;
+    if (lane == 0) { do { v = *pub; } while ((uint32_t)(v >> 32) != (uint32_t)f.pic + 1u); }
+    v = __shfl_sync(FULL, v, 0);
+    const int amvx = (int)(int8_t)(v >> 8), amvy = (int)(int8_t)v;
+    const int kx = (amvx + 2) >> 2, ky = (amvy + 2) >> 2;
+    if ((kx | ky) != 0 && kx >= -15 && kx <= 14 && ky >= -15 && ky <= 15 && test_candidate(kx, ky)) { pred_hit = true; pred_frac = ((amvx | amvy) & 3) != 0; }
+    // new content: the anchor's exhaustive search found nothing (bit 16) and the co-located block is as far off — the search
+    // shrinks to the rows around dy = 0: picking the least bad of 1089 noise candidates buys hardly more than picking it of 160
+    else reduced = ((v >> 16) & 1) != 0 && sad0 >= ME_REFINE_MAX_SAD;
   }
   const bool searched = best == 0xffffffffu;
   if (searched && !window_complete) stage_window();          // predictor rejected: the search needs the whole window
-  if (searched) {
-  // ---- exhaustive search ---------------------------------------------------------------------------
-  uint32_t c[16][4];
-#pragma unroll
-  for (int r = 0; r < 16; r++) {
-    const uint4 v = *reinterpret_cast<const uint4*>(&t.cur_y[r][0]);
-    c[r][0] = v.x; c[r][1] = v.y; c[r][2] = v.z; c[r][3] = v.w;
-  }
-  uint32_t acc[33];
-#pragma unroll
-  for (int i = 0; i < 33; i++) acc[i] = 0;
-  const int wi = lane >> 2, sh = (lane & 3) * 8;
-#pragma unroll
-  for (int y = 0; y < WIN_ROWS; y++) {
-    const uint32_t* wr = sm.win[y] + wi;
-    const uint32_t w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3], w4 = wr[4];
-    const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-      const int dyi = y - r;
-      if (dyi >= 0 && dyi <= 32)
-        acc[dyi] = sad4acc(c[r][0], a0, sad4acc(c[r][1], a1, sad4acc(c[r][2], a2, sad4acc(c[r][3], a3, acc[dyi]))));
-    }
-  }
-  const int bits_x = se_bits_c(4 * (lane - 16));
-#pragma unroll
-  for (int dyi = 0; dyi <= 32; dyi++) {
-    const uint32_t cost = acc[dyi] + (uint32_t)(lambda * (bits_x + se_bits_c(4 * (dyi - 16))));
-    const uint32_t key = (cost << 11) | (uint32_t)(dyi * 32 + lane);
-    best = min(best, key);
-  }
-  best = __reduce_min_sync(FULL, best);
-  }
+  if (searched) best = reduced ? search_rows<ME_NEWCONTENT_DY>(sm, lane, lambda) : search_rows<16>(sm, lane, lambda);
   const int dyi = (best & 2047) >> 5, dxi = best & 31, dx = dxi - 16, dy = dyi - 16;
 
   // ---- quarter-sample refinement (oracle/h264_ref.c encode_inter_mb) ---------------------------------
@@ -337,6 +385,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
       *reinterpret_cast<uint4*>(&t.pred_y[lane][0]) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
     }
   }
+  if (anchor && lane == 0)    // one 8-byte store: tag and vector arrive together
+    *reinterpret_cast<volatile unsigned long long*>(f.me_pub + mb) = ((unsigned long long)((uint32_t)f.pic + 1u) << 32) | ((searched && sad_int >= ME_REFINE_MAX_SAD) ? 0x10000u : 0u) | (uint32_t)((mvx & 0xff) << 8) | (uint32_t)(mvy & 0xff);
 
   // ---- prediction ------------------------------------------------------------------------------------
   {
@@ -397,8 +447,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
 }
 
 int launch_inter(const FrameCtx& f, cudaStream_t st) {
-  const int mbs = f.mbw * f.mbh;
-  k_inter_mb<<<(mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0, st>>>(f);
+  const int warps = f.n_anchor + f.mbw * f.mbh;      // anchors first, then the raster walk (which skips them)
+  k_inter_mb<<<(warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, 0, st>>>(f);
   return 1;
 }
 

@@ -264,7 +264,9 @@ def test_paintover_burst_bit_exact():
         if rc_mode == N.B2V_RC_CQP:
             assert qps[5:8] == [20, 20, 20] and qps[8] == 34 and qps[4] == 34, qps       # trigger after pictures 1..3, two pictures of feedback delay
             # motion never paints; the second static period paints again once its last small refinements have died out
-            assert qps[8:26] == [34] * 18 and qps[26:].count(20) == 3, qps
+            assert qps[8:22] == [34] * 14 and qps[22:].count(20) == 3, qps
+            k = qps.index(20, 22)
+            assert qps[k:k + 3] == [20, 20, 20], qps                                      # ... as one burst
         else:
             assert min(qps[5:8]) == 20, qps
 
