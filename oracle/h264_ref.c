@@ -120,7 +120,7 @@ typedef struct {
   int stripe_fn[MAX_STRIPES];
   int32_t stripe_tab[MAX_STRIPES][3];   /* last picture: byte offset, size, coded flag */
   uint8_t sps_band[2][64]; int sps_band_len[2];   /* [0] regular band, [1] last band (may be shorter / cropped) */
-  int no_i4, no_tpred, no_refine_cap, no_anchor, no_newcontent;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED / B2V_REF_NO_REFINE_CAP, read once at create) */
+  int no_i4, no_tpred, no_refine_cap, no_anchor, no_newcontent, no_zcand;    /* A/B switches for experiments (environment B2V_REF_NO_I4 / B2V_REF_NO_TPRED / B2V_REF_NO_REFINE_CAP, read once at create) */
 } enc_t;
 
 static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -666,10 +666,12 @@ static void anchor_of(const enc_t* e, int mbx, int mby, int* ax, int* ay) {
 }
 static int is_anchor(const enc_t* e, int mbx, int mby) { int ax, ay; anchor_of(e, mbx, mby, &ax, &ay); return ax == mbx && ay == mby; }
 
-/* candidate (cdx,cdy), full-sample: accepted when its SAD is within 4x the noise threshold AND it is a strict local minimum of the
- * cost over its 8 full-sample neighbours AND it costs less than the zero vector; *key = its search key */
+/* candidate (cdx,cdy), full-sample — the zero vector included: "this macroblock did not move last picture" is a prediction too, and
+ * static content whose co-located SAD sits just above the early-termination threshold (noise, text at a coarse QP) would otherwise
+ * run the exhaustive search only to find (0,0) again.  Accepted when its SAD is within 4x the noise threshold AND it is a strict
+ * local minimum of the cost over its 8 full-sample neighbours AND it costs no more than the zero vector; *key = its search key */
 static int try_candidate(const uint8_t cy[256], uint8_t win[48][48], int cdx, int cdy, int lambda, int sad0, uint32_t* key) {
-  if (!(cdx || cdy) || cdx < -15 || cdx > 14 || cdy < -15 || cdy > 15) return 0;
+  if (cdx < -15 || cdx > 14 || cdy < -15 || cdy > 15) return 0;
   uint32_t kc = 0, kmin = 0xffffffffu;
   for (int j = -1; j <= 1; j++)
     for (int i = -1; i <= 1; i++) {
@@ -680,8 +682,8 @@ static int try_candidate(const uint8_t cy[256], uint8_t win[48][48], int cdx, in
       if (i == 0 && j == 0) kc = k; else if (k < kmin) kmin = k;
     }
   const int sadc = (int)(kc >> 11) - lambda * (se_bits(4 * cdx) + se_bits(4 * cdy));
-  const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (16 * 32 + 16);     /* ... and it must beat the zero vector */
-  if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { *key = kc; return 1; }
+  const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (16 * 32 + 16);     /* the zero vector's own key */
+  if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc <= key0) { *key = kc; return 1; }
   return 0;
 }
 
@@ -714,17 +716,19 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
    * threshold AND it is a strict local minimum of the cost over its 8 full-sample neighbours (all inside the search range)
    * AND it costs less than the zero vector (otherwise a stale vector could survive on a scene that has become static);
    * quarter-sample refinement then runs as after a search. */
-  int pred_hit = 0, src_mvx = 0, src_mvy = 0, dyr = 16;      /* src_mv: the vector the accepted candidate was derived from */
+  int pred_hit = 0, src_mvx = 0, src_mvy = 0, dyr = 16, tried_zero = 0;      /* src_mv: the vector the accepted candidate was derived from */
   if (search && prev_type == 1 && !e->no_tpred) {
     const int cdx = asr(prev_mvx + 2, 2), cdy = asr(prev_mvy + 2, 2);
-    if (try_candidate(cy, win, cdx, cdy, lambda, sad0, &best)) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; src_mvx = prev_mvx; src_mvy = prev_mvy; }
+    tried_zero = !(cdx | cdy);
+    if ((!tried_zero || !e->no_zcand) && try_candidate(cy, win, cdx, cdy, lambda, sad0, &best)) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; src_mvx = prev_mvx; src_mvy = prev_mvy; }
   }
   /* anchor predictor: the vector the anchor of this macroblock's 4x4 group found in THIS picture (anchors run first) */
   if (search && !e->no_tpred && !e->no_anchor && !is_anchor(e, mbx, mby)) {
     int ax, ay; anchor_of(e, mbx, mby, &ax, &ay);
     const mb_t* a = &e->mbs[ay * e->mbw + ax];
     const int cdx = asr(a->me_mv[0] + 2, 2), cdy = asr(a->me_mv[1] + 2, 2);
-    if (try_candidate(cy, win, cdx, cdy, lambda, sad0, &best)) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; src_mvx = a->me_mv[0]; src_mvy = a->me_mv[1]; }
+    const int skip_zero = !(cdx | cdy) && (tried_zero || e->no_zcand);      /* the zero vector is not tested twice */
+    if (!skip_zero && try_candidate(cy, win, cdx, cdy, lambda, sad0, &best)) { search = 0; pred_hit = 1; bdx = cdx; bdy = cdy; src_mvx = a->me_mv[0]; src_mvy = a->me_mv[1]; }
     /* new content: the anchor's exhaustive search found no match worth the name and this macroblock's co-located block is as far
      * off — another 1089-candidate search would only pick the least bad of the noise.  The search shrinks to the five rows
      * around dy = 0 (160 candidates: most of what picking a minimum among noise buys, for a sixth of the work). */
@@ -1184,7 +1188,7 @@ void* b2v_ref_enc_create(int width, int height, int slice_rows) {
   e->mbs = (mb_t*)calloc((size_t)e->mbw * e->mbh, sizeof(mb_t));
   e->fb[0].qp = e->fb[1].qp = -1; e->paint_burst = 1;
   e->seg_cols = e->slice_rows == 1 ? auto_seg_cols(e->mbw, e->mbh) : 0;
-  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL; e->no_refine_cap = getenv("B2V_REF_NO_REFINE_CAP") != NULL; e->no_anchor = getenv("B2V_REF_NO_ANCHOR") != NULL; e->no_newcontent = getenv("B2V_REF_NO_NEWCONTENT") != NULL;
+  e->no_i4 = getenv("B2V_REF_NO_I4") != NULL; e->no_tpred = getenv("B2V_REF_NO_TPRED") != NULL; e->no_refine_cap = getenv("B2V_REF_NO_REFINE_CAP") != NULL; e->no_anchor = getenv("B2V_REF_NO_ANCHOR") != NULL; e->no_newcontent = getenv("B2V_REF_NO_NEWCONTENT") != NULL; e->no_zcand = getenv("B2V_REF_NO_ZCAND") != NULL;
   write_param_sets(e);
   return e;
 }

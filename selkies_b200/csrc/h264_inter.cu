@@ -37,6 +37,7 @@ struct alignas(16) InterSm {      // one per warp; the 16-byte size padding keep
 constexpr int ME_PRED_SAD_FACTOR = 4;      // temporal predictor accepted up to 4x the early-termination threshold (and only as a strict local minimum)
 constexpr int ME_FRAC_PENALTY_BITS = 4;   // fractional vectors pay 4 extra bits in the refinement cost
 constexpr int ME_REFINE_MAX_SAD = 8192;   // no sub-sample refinement of a full-sample match this bad
+constexpr int ME_ANCHOR_MAX_POLLS = 1 << 20;   // ~1 s of polling before a macroblock gives up on its anchor
 constexpr int ME_NEWCONTENT_DY = 2;       // vertical range of the reduced search on new content
 
 // Table 8-12 as data: every fractional position is one plane sample or the rounded average of two.
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
   // temporal-predictor test, the refinement around it and the final prediction can touch — 24 rows x 8 words around the predicted
   // position instead of the 48 x 12 window; the rest follows only if the predictor is rejected and the search has to run.
   const int cdx = (prev.mvx + 2) >> 2, cdy = (prev.mvy + 2) >> 2;
-  const bool try_pred = prev.type == MB_P16 && (cdx | cdy) != 0 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15;
+  const bool try_pred = prev.type == MB_P16 && cdx >= -15 && cdx <= 14 && cdy >= -15 && cdy <= 15;     // the zero vector included
   const bool x_inside = x0 >= 16 && x0 + 32 <= f.cw;
   bool window_complete = false;
   auto stage_window = [&]() {
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
     } else stage_window();
   }
   // ---- temporal-predictor early termination (oracle/h264_ref.c encode_inter_mb): the vector this macroblock
-  // had in the previous picture, rounded to full samples (scrolling / panning content repeats it).  Accepted without the
+  // had in the previous picture, rounded to full samples (scrolling / panning content repeats it; the zero vector counts: static
+// content whose co-located SAD sits just above the early-termination threshold would otherwise search only to find (0,0) again).  Accepted without the
   // exhaustive search when its SAD is within 4x the noise threshold AND it is a strict local minimum of the cost over its 8
   // full-sample neighbours AND it costs less than the zero vector; quarter-sample refinement then runs as after a search. ----
   bool pred_hit = false, pred_frac = false, reduced = false;
@@ -286,8 +288,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
       }
     }
     const int sadc = (int)(kc >> 11) - lambda * (se_bits_dev(4 * kx) + se_bits_dev(4 * ky));
-    const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (uint32_t)(16 * 32 + 16);   // ... and it must beat the zero vector
-    if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc < key0) { best = kc; return true; }
+    const uint32_t key0 = ((uint32_t)(sad0 + 2 * lambda) << 11) | (uint32_t)(16 * 32 + 16);   // ... and it must not cost more than the zero vector
+    if (sadc <= ME_PRED_SAD_FACTOR * ME_EARLY_SAD_PER_LAMBDA * lambda && kc < kmin && kc <= key0) { best = kc; return true; }
     return false;
   };
   if (best == 0xffffffffu && try_pred && test_candidate(cdx, cdy)) { pred_hit = true; pred_frac = ((prev.mvx | prev.mvy) & 3) != 0; }
@@ -297,14 +299,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
     if (!window_complete) stage_window();       // overlaps the wait; needed by the search anyway if the candidate is rejected
     const volatile unsigned long long* pub = f.me_pub + (size_t)ay * f.mbw + ax;
     unsigned long long v = 0;
-    if (lane == 0) { do { v = *pub; } while ((uint32_t)(v >> 32) != (uint32_t)f.pic + 1u); }
+    // (bounded: the anchors sit in the lowest-numbered blocks of this grid and never wait, so the value is normally there already or
+    // a few microseconds away; if it never came — a scheduler that does not start blocks in index order — the macroblock goes on
+    // with the exhaustive search: still a valid stream, just not the oracle's choice)
+    if (lane == 0) { int spins = 0; do { v = *pub; } while ((uint32_t)(v >> 32) != (uint32_t)f.pic + 1u && ++spins < ME_ANCHOR_MAX_POLLS); }
     v = __shfl_sync(FULL, v, 0);
+    const bool have = (uint32_t)(v >> 32) == (uint32_t)f.pic + 1u;
     const int amvx = (int)(int8_t)(v >> 8), amvy = (int)(int8_t)v;
     const int kx = (amvx + 2) >> 2, ky = (amvy + 2) >> 2;
-    if ((kx | ky) != 0 && kx >= -15 && kx <= 14 && ky >= -15 && ky <= 15 && test_candidate(kx, ky)) { pred_hit = true; pred_frac = ((amvx | amvy) & 3) != 0; }
+    const bool zero_again = (kx | ky) == 0 && try_pred && (cdx | cdy) == 0;      // the zero vector is not tested twice
+    if (have && !zero_again && kx >= -15 && kx <= 14 && ky >= -15 && ky <= 15 && test_candidate(kx, ky)) { pred_hit = true; pred_frac = ((amvx | amvy) & 3) != 0; }
     // new content: the anchor's exhaustive search found nothing (bit 16) and the co-located block is as far off — the search
     // shrinks to the rows around dy = 0: picking the least bad of 1089 noise candidates buys hardly more than picking it of 160
-    else reduced = ((v >> 16) & 1) != 0 && sad0 >= ME_REFINE_MAX_SAD;
+    else reduced = have && ((v >> 16) & 1) != 0 && sad0 >= ME_REFINE_MAX_SAD;
   }
   const bool searched = best == 0xffffffffu;
   if (searched && !window_complete) stage_window();          // predictor rejected: the search needs the whole window

@@ -13,7 +13,8 @@ from tests import synth                         # noqa: E402
 
 W, H, ND = 3840, 2160, 16
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-frames = [synth.desktop(W, H, t) for t in range(ND)]
+CONTENT = os.environ.get("B2V_CONTENT", "desktop")      # desktop (headline) | gradient (S4) | noise (S2)
+frames = [{"desktop": synth.desktop, "gradient": synth.gradient}[CONTENT](W, H, t) if CONTENT != "noise" else synth.noise(W, H, 100 + t) for t in range(ND)]
 out = {"env": os.environ.get("B2V_CSC", "default")}
 
 

@@ -12,7 +12,8 @@ from tests import synth                         # noqa: E402
 W, H, ND = 3840, 2160, 16
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 gop = int(sys.argv[2]) if len(sys.argv) > 2 else -1
-frames = [synth.desktop(W, H, t) for t in range(ND)]
+CONTENT = os.environ.get("B2V_CONTENT", "desktop")      # desktop (headline) | gradient (S4) | noise (S2)
+frames = [{"desktop": synth.desktop, "gradient": synth.gradient}[CONTENT](W, H, t) if CONTENT != "noise" else synth.noise(W, H, 100 + t) for t in range(ND)]
 with Session(W, H, fps=60.0, rc_mode=N.B2V_RC_CBR, bitrate_kbps=20000, ring_slots=4, gop=gop, collect=False) as s:
     for i, f in enumerate(frames):
         s.resident_upload(i, f)
