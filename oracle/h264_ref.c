@@ -91,7 +91,7 @@ typedef struct {
   int8_t  i16_mode, chroma_mode;
   uint8_t cbp;            /* luma bits 0..3, chroma << 4 */
   int16_t mv[2];          /* quarter-sample units */
-  int8_t  me_bad;         /* motion estimation searched exhaustively and found nothing better than a mean absolute difference of 32: new content */
+  int8_t  me_bad;         /* motion estimation found nothing better than a mean absolute difference of 32 per sample: new content */
   int16_t me_mv[2];       /* what motion estimation chose for this picture (== mv unless the macroblock then became I_PCM); read by the anchor predictor */
   int8_t  i4_modes[16];   /* Intra4x4PredMode per 4x4 block, raster y*4+x (type 3 only) */
 } mb_t;
@@ -757,7 +757,7 @@ static void encode_inter_mb(enc_t* e, const uint8_t* cur_nv12, int mbx, int mby,
   uint8_t Gp[22][22], bq[18][17], hq[17][18], jq[17][17];   /* Gp[v+3][u+3], bq[v+1][u+1], hq[v+1][u+1], jq[v+1][u+1] */
   /* not worth refining when the full-sample match is already within the quantisation noise of this QP */
   const int sad_int = (int)(best >> 11) - lambda * (se_bits(4 * bdx) + se_bits(4 * bdy));
-  m->me_bad = search && sad_int >= ME_REFINE_MAX_SAD;
+  m->me_bad = (search || pred_hit) && sad_int >= ME_REFINE_MAX_SAD;     /* however the vector was found: nothing here matches */
   /* a predictor hit whose previous vector was full-sample is not refined again: the previous refinement already preferred it */
   const int pred_frac = pred_hit && ((src_mvx | src_mvy) & 3);
   /* ... nor when it is hopeless (mean absolute difference of 32 per sample and more: new content, nothing to polish) */

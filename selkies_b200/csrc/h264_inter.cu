@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 5) k_inter_mb(FrameCtx f
     }
   }
   if (anchor && lane == 0)    // one 8-byte store: tag and vector arrive together
-    *reinterpret_cast<volatile unsigned long long*>(f.me_pub + mb) = ((unsigned long long)((uint32_t)f.pic + 1u) << 32) | ((searched && sad_int >= ME_REFINE_MAX_SAD) ? 0x10000u : 0u) | (uint32_t)((mvx & 0xff) << 8) | (uint32_t)(mvy & 0xff);
+    *reinterpret_cast<volatile unsigned long long*>(f.me_pub + mb) = ((unsigned long long)((uint32_t)f.pic + 1u) << 32) | (sad_int >= ME_REFINE_MAX_SAD ? 0x10000u : 0u) | (uint32_t)((mvx & 0xff) << 8) | (uint32_t)(mvy & 0xff);
 
   // ---- prediction ------------------------------------------------------------------------------------
   {
