@@ -55,3 +55,19 @@ def desktop(w, h, t=0, seed=1):
     f[y0:, w // 6: w // 6 + region.shape[1], 1] = region
     f[y0:, w // 6: w // 6 + region.shape[1], 2] = region
     return f
+
+
+def predictor_paths(w, h):
+    """Eleven pictures that walk every exit of the P-picture motion search: a still (zero-motion exit), the same with
+    +-2 LSB noise (zero-vector candidate), the onset of a scroll (anchors search, their groups take the anchor's vector), the scroll
+    going on (temporal predictor), a cut to noise (new content: anchors search, the rest run the reduced search), noise again, and back
+    to the still."""
+    still = desktop(w, h, 0)
+
+    def jitter(seed):
+        rng = np.random.default_rng(seed)
+        f = still.astype(np.int16)
+        f[..., :3] += rng.integers(-2, 3, (h, w, 3), dtype=np.int16)
+        return np.clip(f, 0, 255).astype(np.uint8)
+    return ([still, still, jitter(1), jitter(2)] + [desktop(w, h, t) for t in (1, 2, 3)]
+            + [noise(w, h, 40), noise(w, h, 41), still, still])

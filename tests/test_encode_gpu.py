@@ -67,6 +67,13 @@ def test_motion_and_noise_bit_exact():
     assert_same(*encode_both(192, 112, frames, qp=22, slice_rows=2))
 
 
+@pytest.mark.parametrize("w,h,qp,slice_rows", [(320, 192, 30, 1), (130, 70, 22, 1), (208, 144, 44, 2), (640, 368, 36, 1)])
+def test_motion_search_exits_bit_exact(w, h, qp, slice_rows):
+    """Every exit of k_inter_mb's motion search — zero-motion, zero-vector / temporal / anchor candidates, the reduced search on new
+    content, the exhaustive search — incl. sizes whose 4x4 macroblock groups are clamped at the right / bottom edge (synth.predictor_paths)."""
+    assert_same(*encode_both(w, h, synth.predictor_paths(w, h), qp=qp, slice_rows=slice_rows))
+
+
 @pytest.mark.parametrize("qp,slice_rows", [(0, 1), (6, 2), (14, 1)])
 def test_pcm_fallback_bit_exact(qp, slice_rows):
     """Macroblocks whose CAVLC size bound exceeds 3200 bits are sent as I_PCM (I and P slices)."""

@@ -87,6 +87,26 @@ def test_motion_is_found():
     assert len(aus[1]) < len(aus[0]) // 3
 
 
+@pytest.mark.parametrize("w,h,qp", [(320, 192, 30), (130, 70, 22), (208, 144, 44)])
+def test_motion_search_exits_decode(w, h, qp):
+    """Every exit of the P-picture motion search (zero-motion, zero-vector / temporal / anchor candidates, reduced search on new
+    content, exhaustive search) on sizes whose 4x4 macroblock groups are clamped at the right / bottom edge."""
+    aus, _ = run(w, h, synth.predictor_paths(w, h), qp)
+    assert len(aus[1]) < 200 and len(aus[10]) < len(aus[9]) // 10          # a still costs next to nothing
+
+
+def test_anchor_predictor_saves_nothing_but_time(monkeypatch):
+    """The anchor / zero-vector candidates and the reduced search are shortcuts: against the same encoder with all three switched
+    off (every non-static macroblock searched exhaustively) the stream may differ, but not by more than a few percent of bits."""
+    w, h, qp = 320, 192, 30
+    frames = synth.predictor_paths(w, h)
+    fast = sum(len(a) for a in run(w, h, frames, qp)[0][1:])
+    for k in ("B2V_REF_NO_ANCHOR", "B2V_REF_NO_NEWCONTENT", "B2V_REF_NO_ZCAND"):
+        monkeypatch.setenv(k, "1")
+    slow = sum(len(a) for a in run(w, h, frames, qp)[0][1:])
+    assert abs(fast - slow) <= 0.03 * slow
+
+
 def test_psnr_reasonable():
     f = synth.desktop(320, 192, 0)
     aus, dec = run(320, 192, [f], 24)
