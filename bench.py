@@ -358,7 +358,7 @@ def live_csc_traffic(timeout_s=240):
 def workload_config(frames_per_step):
     return {"workload": "C2: 3840x2160 synthetic desktop BGRA -> fused BT.709 CSC -> H.264 CBP (IDR then P; full-sample ME +-16: zero / temporal / anchor predictors in front of an exhaustive search, quarter-sample refinement; Intra4x4/16x16 in IDR; CAVLC)",
             "frames_per_step": frames_per_step, "rate_control": f"CBR {BITRATE_KBPS} kbit/s @ {FPS_NOMINAL:g} fps nominal, free-running",
-            "slice_rows": 1, "sessions_per_gpu": 1,
+            "slice_rows": "default (P pictures: 8 macroblock rows per slice, IDR pictures: sub-row slices)", "sessions_per_gpu": 1,
             "l2_policy": f"inputs larger than L2: {N_DISTINCT} distinct frames x 33.2 MB cycled", "parallelism": "one independent session per GPU (no collective)"}
 
 

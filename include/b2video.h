@@ -64,7 +64,8 @@ typedef struct b2v_settings {
   int32_t gop;              /* in FRAMES.  <=0: IDR only on request (settings.py:163 keyframe_distance=-1);
                                1: intra-only; N: IDR every N frames.  keyframe_distance itself is in SECONDS:
                                the host side passes round(seconds * fps) (pixelflux_compat.py)             */
-  int32_t slice_rows;       /* macroblock rows per slice (>=1); 0 = library default (1)      */
+  int32_t slice_rows;       /* macroblock rows per slice of a P picture (>=1); 0 = default: 8, or one slice per stripe in striped
+                               mode (inside a slice P_Skip infers moving vectors: a scrolling picture costs half the bytes) */
   int32_t header_mode;      /* B2V_HDR_*                                                    */
   int32_t ring_slots;       /* pinned BGRA ingest ring depth (2..16); 0 = default 4          */
   int32_t flags;            /* B2V_FLAG_*                                                   */
@@ -79,7 +80,7 @@ typedef struct b2v_settings {
                                delivered by its own callback with y_start/height (10-byte header bytes 4..9,
                                selkies-ws-core.js:3183-3196); a stripe whose macroblocks were all skipped is not
                                delivered.  0 or >= picture rows = full frame */
-  int32_t idr_slice_mbs;    /* IDR pictures only, slice_rows == 1 only: macroblocks per slice INSIDE a row.  The macroblocks of an
+  int32_t idr_slice_mbs;    /* IDR pictures only (whatever slice_rows is): macroblocks per slice INSIDE a row.  The macroblocks of an
                                intra slice are a serial chain (left-neighbour prediction), so shorter slices shorten the chain the
                                GPU has to walk (a 4K key frame: 3.3 ms with whole rows).  0 = default (about 540 slices per
                                picture, none under 30 macroblocks: 60 at 4K, 30 at 1080p), < 0 = whole rows, n = n macroblocks */

@@ -95,7 +95,7 @@ def jpeg_encode_bgra(bgra: np.ndarray, quality: int) -> bytes:
 class RefEncoder:
     """ctypes wrapper of oracle/h264_ref.c (one encoder instance)."""
 
-    def __init__(self, width: int, height: int, slice_rows: int = 1):
+    def __init__(self, width: int, height: int, slice_rows: int = 0):
         L = lib()
         L.b2v_ref_enc_create.restype = C.c_void_p
         L.b2v_ref_enc_create.argtypes = [C.c_int, C.c_int, C.c_int]

@@ -187,7 +187,7 @@ int alloc_geometry(Session* s) {
   } else if (s->encode) {
     EncoderConfig ec{};
     ec.width = s->dst_w; ec.height = s->dst_h; ec.coded_w = s->coded_w; ec.coded_h = s->coded_h;
-    ec.slice_rows = s->cfg.slice_rows > 0 ? s->cfg.slice_rows : 1;
+    ec.slice_rows = s->cfg.slice_rows;          // <= 0: the encoder's default rule
     ec.sm_count = s->sm_count;
     ec.stripe_rows = s->cfg.stripe_rows > 0 ? s->cfg.stripe_rows : 0;
     ec.idr_slice_mbs = s->cfg.idr_slice_mbs;

@@ -51,6 +51,7 @@ __device__ const int32_t rc_qs[52] = {
   1290, 1448, 1625, 1825, 2048, 2299, 2580, 2896, 3251, 3649, 4096, 4598, 5161, 5793, 6502, 7298, 8192, 9195, 10321, 11585, 13004,
   14596, 16384, 18390, 20643, 23170};
 
+struct ChunkAgg; struct ChunkInc;
 struct FrameCtx {          // everything a kernel needs about the picture being coded
   int cw, ch, mbw, mbh, slice_rows, n_slices;   // n_slices: of THIS picture
   int seg_cols;            // > 0 (IDR pictures with slice_rows == 1 only): slices of seg_cols macroblocks inside a row — the macroblocks
@@ -80,6 +81,9 @@ struct FrameCtx {          // everything a kernel needs about the picture being 
   uint32_t* slice_rbsp;    // [n_slices] RBSP bytes before emulation prevention
   long long* slice_bits;   // [n_slices]
   int* progress;           // [mbh] intra wavefront progress counters
+  int chunks_per_slice;    // k_slice_build: blocks per slice (chunks of up to 256 macroblocks), set at launch
+  struct ChunkAgg* chunk_agg; struct ChunkInc* chunk_inc;   // [chunks] look-back records of k_slice_build
+  int* slice_done;         // [n_slices] chunks of the slice that have finished copying (reset by the last one)
   RcState* rc;
   const uint8_t* param_sets; int param_len;   // SPS+PPS NAL bytes (IDR pictures)
   // bands ("stripes", pixelflux h264_fullframe = False): groups of band_rows macroblock rows, each an independent H.264

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "h264_common.cuh"
+#include <algorithm>
 #include "h264_encoder.h"
 #include "h264_kernels.h"
 
@@ -30,6 +31,7 @@ struct Encoder {
   int16_t* coef[2] = {nullptr, nullptr};
   uint8_t* nnz[2] = {nullptr, nullptr};
   long long* mb_off = nullptr; int* mb_run = nullptr;
+  void *chunk_agg = nullptr, *chunk_inc = nullptr; int* slice_done = nullptr;   // k_slice_build look-back records (h264_entropy.cu)
   unsigned long long* me_pub = nullptr;   // anchor macroblocks' vectors of the picture being analysed (h264_inter.cu)
   uint32_t *mb_words = nullptr, *mb_nbits = nullptr, *slice_buf = nullptr, *slice_size = nullptr, *slice_rbsp = nullptr;
   long long* slice_bits = nullptr;
@@ -127,14 +129,22 @@ std::vector<uint8_t> make_param_sets(const EncoderConfig& c, int mbw, int mbh, i
        if (e_ != cudaSuccess) { snprintf(g_enc_err, sizeof g_enc_err, "%s -> %s", #call, cudaGetErrorString(e_)); encoder_destroy(e); return -2; } \
   } while (0)
 
-int encoder_create(const EncoderConfig* cfg, Encoder** out) {
-  if (!cfg || !out || (cfg->coded_w & 15) || (cfg->coded_h & 15) || cfg->slice_rows < 1) {
+int encoder_create(const EncoderConfig* cfg_in, Encoder** out) {
+  if (!cfg_in || !out || (cfg_in->coded_w & 15) || (cfg_in->coded_h & 15)) {
     snprintf(g_enc_err, sizeof g_enc_err, "bad encoder config");
     return -1;
   }
   Encoder* e = new Encoder();
-  e->cfg = *cfg;
-  e->mbw = cfg->coded_w / 16; e->mbh = cfg->coded_h / 16;
+  e->cfg = *cfg_in;
+  e->mbw = cfg_in->coded_w / 16; e->mbh = cfg_in->coded_h / 16;
+  // slice_rows <= 0: the default rule (oracle/h264_ref.c b2v_ref_enc_create): P pictures in slices of 8 macroblock rows, one slice per
+  // band in striped mode — inside a slice the row above predicts the motion vector and P_Skip infers a moving one, which halves the
+  // bytes of a scrolling picture against one row per slice.  IDR pictures are sliced on their own (seg_cols below).
+  if (e->cfg.slice_rows <= 0) {
+    const bool striped = e->cfg.stripe_rows > 0 && e->cfg.stripe_rows < e->mbh;
+    e->cfg.slice_rows = striped ? e->cfg.stripe_rows : (e->mbh < 8 ? e->mbh : 8);
+  }
+  const EncoderConfig* cfg = &e->cfg;
   e->n_slices = (e->mbh + cfg->slice_rows - 1) / cfg->slice_rows;
   const size_t mbs = (size_t)e->mbw * e->mbh, fb = (size_t)cfg->coded_w * cfg->coded_h * 3 / 2;
   ECK(cudaMalloc((void**)&e->recon[0], fb));
@@ -159,10 +169,11 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMalloc((void**)&e->mb_run, mbs * sizeof(int)));
   e->slice_words = cfg->slice_rows * e->mbw * MB_WORDS + 64;
   // IDR pictures: slices shorter than a row (same rule as oracle/h264_ref.c auto_seg_cols: about 540 slices, none under 30 macroblocks)
-  if (cfg->slice_rows == 1 && cfg->idr_slice_mbs >= 0) {
+  // (idr_slice_mbs < 0: IDR pictures in slices of slice_rows whole rows, like P pictures — rows of a slice then wait on the row above)
+  if (cfg->idr_slice_mbs >= 0) {
     int cols = cfg->idr_slice_mbs;
-    if (cols == 0) { int segs = 540 / e->mbh; const int cap = e->mbw / 30; if (segs > cap) segs = cap; cols = segs <= 1 ? 0 : (e->mbw + segs - 1) / segs; }
-    if (cols >= e->mbw) cols = 0;
+    if (cols == 0) { int segs = 540 / e->mbh; const int cap = e->mbw / 30; if (segs > cap) segs = cap; cols = segs <= 1 ? e->mbw : (e->mbw + segs - 1) / segs; }
+    if (cols >= e->mbw) cols = e->mbw;          // one slice per macroblock row
     e->seg_cols = cols;
   }
   if (e->seg_cols) { e->n_seg_slices = e->mbh * ((e->mbw + e->seg_cols - 1) / e->seg_cols); e->seg_slice_words = e->seg_cols * MB_WORDS + 64; }
@@ -174,6 +185,13 @@ int encoder_create(const EncoderConfig* cfg, Encoder** out) {
   ECK(cudaMalloc((void**)&e->slice_size, nsl_max * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->slice_rbsp, nsl_max * sizeof(uint32_t)));
   ECK(cudaMalloc((void**)&e->slice_bits, nsl_max * sizeof(long long)));
+  {   // k_slice_build's look-back records: one per chunk of up to 256 macroblocks (32 bytes cover either record type)
+    const size_t cps_row = ((size_t)cfg->slice_rows * e->mbw + 255) / 256, cps_seg = e->seg_cols ? ((size_t)e->seg_cols + 255) / 256 : 0;
+    const size_t chunks = std::max((size_t)e->n_slices * cps_row, (size_t)e->n_seg_slices * cps_seg) + 1;
+    ECK(cudaMalloc((void**)&e->chunk_agg, chunks * 32)); ECK(cudaMemset(e->chunk_agg, 0, chunks * 32));
+    ECK(cudaMalloc((void**)&e->chunk_inc, chunks * 32)); ECK(cudaMemset(e->chunk_inc, 0, chunks * 32));
+    ECK(cudaMalloc((void**)&e->slice_done, nsl_max * sizeof(int))); ECK(cudaMemset(e->slice_done, 0, nsl_max * sizeof(int)));
+  }
   ECK(cudaMalloc((void**)&e->progress, e->mbh * sizeof(int)));
   ECK(cudaMalloc((void**)&e->overflow, sizeof(int)));
   ECK(cudaMemset(e->overflow, 0, sizeof(int)));
@@ -213,7 +231,7 @@ void encoder_destroy(Encoder* e) {
   if (!e) return;
   void* ptrs[] = {e->recon[0], e->recon[1], e->mbinfo[0], e->mbinfo[1], e->coef[0], e->coef[1], e->nnz[0], e->nnz[1], e->mb_words, e->mb_nbits, e->slice_buf,
                   e->slice_size, e->slice_rbsp, e->slice_bits, e->progress, e->overflow, e->rc, e->param_sets, e->mb_off, e->mb_run, e->i4modes[0],
-                  e->i4modes[1], e->band_fn, e->band_coded, e->me_pub};
+                  e->i4modes[1], e->band_fn, e->band_coded, e->me_pub, e->chunk_agg, e->chunk_inc, e->slice_done};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int b = 0; b < 2; b++) {
     if (e->ev_analysed[b]) cudaEventDestroy(e->ev_analysed[b]);
@@ -241,6 +259,7 @@ int encoder_encode(Encoder* e, const EncodeFrameParams* p, cudaStream_t st) {
   f.cur = p->cur; f.ref = e->recon[e->cur ^ 1]; f.recon = e->recon[e->cur];
   f.mbinfo = e->mbinfo[par]; f.mbinfo_prev = e->mbinfo[par ^ 1]; f.i4modes = e->i4modes[par]; f.coef = e->coef[par]; f.nnz = e->nnz[par];
   f.me_pub = e->me_pub;
+  f.chunk_agg = (ChunkAgg*)e->chunk_agg; f.chunk_inc = (ChunkInc*)e->chunk_inc; f.slice_done = e->slice_done; f.chunks_per_slice = 1;
   {   // anchors: ceil(mbw/4) columns x (groups of 4 rows inside every band)
     const int rows_last = e->mbh - (e->n_bands - 1) * e->band_rows;
     f.n_anchor = ((e->mbw + 3) / 4) * ((e->n_bands - 1) * ((e->band_rows + 3) / 4) + (rows_last + 3) / 4);

@@ -17,6 +17,8 @@
 #include "h264_cavlc.cuh"
 #include "h264_encoder.h"
 #include "h264_kernels.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace b2v {
 
@@ -442,9 +444,9 @@ __device__ __forceinline__ void slice_copy_body(const FrameCtx& f) {
 
 // ---- k_slice_ep: one block per slice counts the emulation-prevention bytes the slice needs (7.4.1): a 03 goes in
 // front of byte i iff byte <= 3 and the run of zero bytes before it is even and >= 2.
-__device__ __forceinline__ void slice_ep_body(const FrameCtx& f) {
+__device__ __forceinline__ void slice_ep_body(const FrameCtx& f, int s) {
   __shared__ int s_red[SLICE_THREADS / 32];
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
   const long long rbsp_bytes = __ldcg(&f.slice_rbsp[s]);
   int ep = 0;
@@ -477,14 +479,260 @@ __device__ __forceinline__ void slice_ep_body(const FrameCtx& f) {
 // copy -> emulation-prevention count.  The block's own global writes (macroblock offsets, the RBSP words built with atomicOr) are
 // visible to it after a fence + barrier.
 static_assert(SLICE_THREADS == COPY_THREADS, "one block shape for the fused slice kernel");
-__global__ void __launch_bounds__(SLICE_THREADS) k_slice_build(FrameCtx f) {
+__global__ void __launch_bounds__(SLICE_THREADS) k_slice_build_v1(FrameCtx f) {
   slice_scan_body(f);
   __threadfence();
   __syncthreads();
   slice_copy_body(f);
   __threadfence();
   __syncthreads();
-  slice_ep_body(f);
+  slice_ep_body(f, blockIdx.x);
+}
+
+
+// ---- k_slice_build (chunked): one block per CHUNK of up to 256 consecutive macroblocks of a slice, so a slice of many rows is built
+// by many blocks instead of one long loop.  What a chunk needs from the chunks in front of it is (a) the bit position where it starts
+// and (b) the mb_skip_run still open at that point — the first coded macroblock of a chunk codes ue(open run + its own leading skips),
+// whose LENGTH is the only thing in a chunk that depends on the carry.  Decoupled look-back (the chunks of a slice are consecutive
+// blocks of this grid, lower-numbered blocks never wait for higher ones): every chunk publishes its AGGREGATE as soon as its local
+// scans are done (has a coded macroblock?  skips in front of the first / behind the last one, bits of everything but that one ue),
+// folds the aggregates of its predecessors — or starts from the nearest published INCLUSIVE state — and publishes its own inclusive
+// state.  A chunk that holds an I_PCM macroblock (byte alignment: its length depends on its position) publishes no usable aggregate;
+// its successors wait for its inclusive state instead.  Then every chunk shifts its macroblocks' bit strings into the slice RBSP
+// (8 threads per macroblock, offsets from shared memory), the chunk that holds the slice's last macroblock appends the trailing
+// skip run + rbsp_trailing_bits, and the last chunk of a slice to FINISH counts the slice's emulation-prevention bytes.
+struct ChunkAgg { int flag; int has; int first_run; int trailing; long long rest_bits; };   // has: bit 0 coded macroblock present, bit 1 I_PCM inside (no aggregate)
+struct ChunkInc { int flag; int trailing; long long bits; };
+constexpr int CHUNK_MAX_POLLS = 1 << 22;
+
+__device__ __forceinline__ bool wait_flag(const volatile int* flag, int tag) {
+  int spins = 0;
+  while (*flag != tag) if (++spins > CHUNK_MAX_POLLS) return false;
+  __threadfence();
+  return true;
+}
+
+__global__ void __launch_bounds__(SLICE_THREADS, 8) k_slice_build(FrameCtx f) {
+  __shared__ long long s_warp_sum[SLICE_THREADS / 32];
+  __shared__ int s_warp_max[SLICE_THREADS / 32];
+  __shared__ uint32_t s_nb[SLICE_THREADS];       // nbits | I_PCM flag (bit 30), 0xffffffff = skipped
+  __shared__ int s_run[SLICE_THREADS];
+  __shared__ long long s_off[SLICE_THREADS];
+  __shared__ long long s_bits_in, s_bits_out;
+  __shared__ int s_trail_in, s_trail_out, s_first, s_flag;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cps = f.chunks_per_slice, s = blockIdx.x / cps, k = blockIdx.x - s * cps;
+  const SliceGeo geo = slice_geo(f, s);
+  const int n_chunks = (geo.n_mb + SLICE_THREADS - 1) / SLICE_THREADS;
+  const int tag = f.pic + 1, qp = frame_qp(f);
+  uint32_t* out = f.slice_buf + (size_t)s * f.slice_words;
+  bool active = k < n_chunks;
+  const int idx0 = k * SLICE_THREADS, n = active ? min(SLICE_THREADS, geo.n_mb - idx0) : 0, mb_first = geo.mb0 + idx0;
+  const bool last_chunk = active && k == n_chunks - 1;
+  if (active) {
+    // ---- local scans -------------------------------------------------------------------------------------------------------
+    uint32_t nbits = 0; bool skip = true, pcm = false;
+    if (tid < n) { const uint32_t v = f.mb_nbits[mb_first + tid]; skip = (v >> 31) != 0; pcm = ((v >> 30) & 1u) != 0; nbits = v & 0x3fffffffu; }
+    const bool any_pcm = __syncthreads_or(pcm) != 0;
+    int incl_max = skip ? -1 : tid;            // last coded macroblock (local index) up to and including this one
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl_max, d); if (lane >= d) incl_max = max(incl_max, o); }
+    if (lane == 31) s_warp_max[warp] = incl_max;
+    __syncthreads();
+    int prev_max = -1, last_coded = -1;
+    for (int w = 0; w < SLICE_THREADS / 32; w++) { if (w < warp) prev_max = max(prev_max, s_warp_max[w]); last_coded = max(last_coded, s_warp_max[w]); }
+    int excl_max = __shfl_up_sync(FULL, incl_max, 1);
+    if (lane == 0) excl_max = -1;
+    excl_max = max(excl_max, prev_max);
+    const bool first_coded = !skip && excl_max < 0;
+    if (tid == 0) s_first = n;                 // skips in front of the first coded macroblock (n: none coded)
+    __syncthreads();
+    if (first_coded) s_first = tid;
+    const int run_local = tid - 1 - excl_max;  // for every coded macroblock but the first: its mb_skip_run
+    const int pre = (!skip && !first_coded && !f.idr) ? ue_len((uint32_t)run_local) : 0;
+    const long long tot = skip ? 0 : (long long)pre + nbits;
+    long long incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const long long o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    long long woff = 0, rest = 0;
+    for (int w = 0; w < SLICE_THREADS / 32; w++) { if (w < warp) woff += s_warp_sum[w]; rest += s_warp_sum[w]; }
+    const long long off_local = woff + incl - tot;       // bits of this chunk in front of the macroblock, without the first ue
+    const int first = s_first, trailing_local = last_coded >= 0 ? n - 1 - last_coded : n;
+    // ---- publish the aggregate, get the carry --------------------------------------------------------------------------------
+    if (tid == 0) {
+      ChunkAgg* a = f.chunk_agg + blockIdx.x;
+      a->has = (last_coded >= 0 ? 1 : 0) | (any_pcm ? 2 : 0); a->first_run = first; a->trailing = trailing_local; a->rest_bits = rest;
+      __threadfence();
+      *reinterpret_cast<volatile int*>(&a->flag) = tag;
+    }
+    if (warp == 0) {
+      // base state in front of chunk 0: the slice header (every chunk can size it: no waiting for chunk 0)
+      long long bits; int trail = 0; bool ok = true;
+      {
+        CountSink h;
+        const int band = geo.row0 / f.band_rows;
+        slice_header(h, f, geo.mb0 - band * f.band_rows * f.mbw, qp, f.idr ? 0 : f.striped ? f.band_fn[band] : f.frame_num);
+        bits = h.n;
+      }
+      int start = 0;
+      // nearest predecessor whose inclusive state is already there (32 at a time, nearest first)
+      for (int hi = k - 1; hi >= 0 && start == 0; hi -= 32) {
+        const int j = hi - lane;
+        const bool ready = j >= 0 && *reinterpret_cast<const volatile int*>(&f.chunk_inc[blockIdx.x - k + j].flag) == tag;
+        const unsigned m = __ballot_sync(FULL, ready);
+        if (m) {
+          const int jj = hi - (__ffs(m) - 1);
+          __threadfence();
+          const ChunkInc* c = f.chunk_inc + (blockIdx.x - k + jj);
+          bits = *reinterpret_cast<const volatile long long*>(&c->bits); trail = *reinterpret_cast<const volatile int*>(&c->trailing);
+          start = jj + 1;
+        }
+      }
+      // fold the aggregates of chunks start .. k-1, 32 loads at a time
+      for (int base = start; base < k; base += 32) {
+        const int j = base + lane;
+        int has = 0, fr = 0, tr = 0; long long rb = 0, ib = 0; int it = 0;
+        if (j < k) {
+          const ChunkAgg* a = f.chunk_agg + (blockIdx.x - k + j);
+          ok &= wait_flag(&a->flag, tag);
+          has = *reinterpret_cast<const volatile int*>(&a->has);
+          if (has & 2) {                       // I_PCM inside: only its inclusive state will do
+            const ChunkInc* c = f.chunk_inc + (blockIdx.x - k + j);
+            ok &= wait_flag(&c->flag, tag);
+            ib = *reinterpret_cast<const volatile long long*>(&c->bits); it = *reinterpret_cast<const volatile int*>(&c->trailing);
+          } else {
+            fr = *reinterpret_cast<const volatile int*>(&a->first_run); tr = *reinterpret_cast<const volatile int*>(&a->trailing);
+            rb = *reinterpret_cast<const volatile long long*>(&a->rest_bits);
+          }
+        }
+        const int cnt = min(32, k - base);
+        for (int t = 0; t < cnt; t++) {
+          const int h2 = __shfl_sync(FULL, has, t), fr2 = __shfl_sync(FULL, fr, t), tr2 = __shfl_sync(FULL, tr, t);
+          const long long rb2 = __shfl_sync(FULL, rb, t), ib2 = __shfl_sync(FULL, ib, t); const int it2 = __shfl_sync(FULL, it, t);
+          const int n_j = min(SLICE_THREADS, geo.n_mb - (base + t) * SLICE_THREADS);
+          if (h2 & 2) { bits = ib2; trail = it2; }
+          else if (h2 & 1) { bits += (f.idr ? 0 : ue_len((uint32_t)(trail + fr2))) + rb2; trail = tr2; }
+          else trail += n_j;
+        }
+      }
+      ok = __all_sync(FULL, ok);
+      if (lane == 0) { s_bits_in = bits; s_trail_in = trail; if (!ok) atomicExch(f.overflow, 4); }
+    }
+    __syncthreads();
+    const long long bits_in = s_bits_in; const int trail_in = s_trail_in;
+    // ---- final offsets ----------------------------------------------------------------------------------------------------------
+    const int run_first = trail_in + first;
+    const int pre_first = (last_coded >= 0 && !f.idr) ? ue_len((uint32_t)run_first) : 0;
+    int run = first_coded ? run_first : run_local;
+    long long my_off = bits_in + off_local + ((!skip && !first_coded) ? pre_first : 0);
+    s_nb[tid] = skip ? 0xffffffffu : (nbits | (pcm ? 0x40000000u : 0u)); s_run[tid] = run; s_off[tid] = my_off;
+    if (tid == 0) { s_bits_out = bits_in + rest + pre_first; s_trail_out = last_coded >= 0 ? trailing_local : trail_in + n; }
+    __syncthreads();
+    if (any_pcm && tid == 0) {                   // byte alignment of the raw samples: serial walk (pathological content only)
+      long long pos = bits_in;
+      for (int j = 0; j < n; j++) {
+        const uint32_t nb = s_nb[j];
+        if (nb == 0xffffffffu) continue;
+        s_off[j] = pos;
+        pos += (f.idr ? 0 : ue_len((uint32_t)s_run[j])) + (nb & 0x3fffffffu);
+        if (nb & 0x40000000u) pos = ((pos + 7) & ~7LL) + 384 * 8;
+      }
+      s_bits_out = pos;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      ChunkInc* c = f.chunk_inc + blockIdx.x;
+      c->bits = s_bits_out; c->trailing = s_trail_out;
+      __threadfence();
+      *reinterpret_cast<volatile int*>(&c->flag) = tag;
+      if (k == 0) {                              // slice header (the bits it occupies were counted above)
+        GlobalSink g{out, 0};
+        const int band = geo.row0 / f.band_rows;
+        slice_header(g, f, geo.mb0 - band * f.band_rows * f.mbw, qp, f.idr ? 0 : f.striped ? f.band_fn[band] : f.frame_num);
+      }
+      if (last_chunk) {                          // trailing mb_skip_run, rbsp_trailing_bits
+        GlobalSink g{out, s_bits_out};
+        const int runt = s_trail_out;
+        if (!f.idr && runt > 0) put_ue(g, (uint32_t)runt);
+        f.slice_bits[s] = g.pos;
+        if (runt < geo.n_mb) {                   // the slice holds a coded macroblock (benign races: every writer stores the same value)
+          f.rc->pic_coded = 1;
+          if (f.striped) f.band_coded[geo.row0 / f.band_rows] = 1;
+        }
+        g.put(1, 1);
+        f.slice_rbsp[s] = (uint32_t)((g.pos + 7) >> 3);
+      }
+    }
+  }
+  // ---- the last block of the picture to get here runs the rate-control step (every block read its QP at its start) --------------
+  if (tid == 0) {
+    __threadfence();
+    s_flag = atomicAdd(&f.rc->scan_done, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_flag) {
+    __threadfence();
+    long long bits = 0;
+    for (int j = tid; j < f.n_slices; j += SLICE_THREADS) bits += __ldcg(&f.slice_bits[j]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(FULL, bits, d);
+    __syncthreads();
+    if (lane == 0) s_warp_sum[warp] = bits;
+    __syncthreads();
+    if (tid == 0) {
+      long long t = 0;
+      for (int w = 0; w < SLICE_THREADS / 32; w++) t += s_warp_sum[w];
+      f.rc->scan_done = 0;
+      rc_step(f, qp, t);
+    }
+  }
+  if (!active) return;
+  // ---- copy: COPY_LANES threads per macroblock shift its bit string into the slice RBSP ----------------------------------------
+  {
+    const int sub = tid % COPY_LANES;
+    for (int i = tid / COPY_LANES; i < n; i += SLICE_THREADS / COPY_LANES) {
+      const uint32_t v = s_nb[i];
+      if (v == 0xffffffffu) continue;            // P_Skip: folded into a later mb_skip_run
+      const bool pcm = (v & 0x40000000u) != 0;
+      const uint32_t nbits = v & 0x3fffffffu;
+      const int mb = mb_first + i, mby = mb / f.mbw, mbx = mb - mby * f.mbw;
+      long long pos = s_off[i];
+      if (!f.idr) {
+        const uint32_t run = (uint32_t)s_run[i];
+        if (sub == 0) { GlobalSink g{out, pos}; put_ue(g, run); }
+        pos += ue_len(run);
+      }
+      const uint32_t* src = f.mb_words + (size_t)mb * MB_WORDS;
+      for (int w = sub; w < (int)((nbits + 31) >> 5); w += COPY_LANES) or_word(out, pos + 32LL * w, src[w]);
+      if (pcm) {     // I_PCM payload: 256 luma, 64 Cb, 64 Cr samples from the reconstruction (== source), byte aligned
+        const long long pp = (pos + nbits + 7) & ~7LL;
+        const int px = mbx * 16, py = mby * 16;
+        const uint8_t* ry = f.recon; const uint8_t* ruv = f.recon + (size_t)f.cw * f.ch;
+        for (int w = sub; w < 96; w += COPY_LANES) {
+          uint32_t q;
+          if (w < 64) q = __byte_perm(__ldcg(reinterpret_cast<const uint32_t*>(ry + (size_t)(py + (w >> 2)) * f.cw + px + (w & 3) * 4)), 0, 0x0123);
+          else {
+            const int kk = (w - 64) & 15, comp = (w - 64) >> 4;
+            const uint2 c2 = __ldcg(reinterpret_cast<const uint2*>(ruv + (size_t)(py / 2 + (kk >> 1)) * f.cw + px + (kk & 1) * 8));
+            q = comp == 0 ? __byte_perm(c2.x, c2.y, 0x0246) : __byte_perm(c2.x, c2.y, 0x1357);
+          }
+          or_word(out, pp + 32LL * w, q);
+        }
+      }
+    }
+  }
+  // ---- the chunk of a slice that finishes last counts the slice's emulation-prevention bytes --------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const bool lastf = atomicAdd(&f.slice_done[s], 1) == n_chunks - 1;
+    if (lastf) f.slice_done[s] = 0;
+    s_flag = lastf;
+  }
+  __syncthreads();
+  if (s_flag) { __threadfence(); slice_ep_body(f, s); }
 }
 
 // ------------------------------------------------------------------------------------------------ k_pack_au
@@ -613,7 +861,12 @@ int launch_cavlc(const FrameCtx& f, cudaStream_t st) {
   return 1;
 }
 int launch_slice_scan(const FrameCtx& f, cudaStream_t st) {
-  k_slice_build<<<f.n_slices, SLICE_THREADS, 0, st>>>(f);      // scan + copy + emulation-prevention count
+  static const bool v1 = getenv("B2V_SLICE_KERNEL") && !strcmp(getenv("B2V_SLICE_KERNEL"), "v1");   // A/B: one block per slice
+  if (v1) { k_slice_build_v1<<<f.n_slices, SLICE_THREADS, 0, st>>>(f); return 1; }
+  FrameCtx g = f;
+  const int full = f.seg_cols ? f.seg_cols : f.slice_rows * f.mbw;       // macroblocks of a full-size slice of this picture
+  g.chunks_per_slice = (full + SLICE_THREADS - 1) / SLICE_THREADS;
+  k_slice_build<<<f.n_slices * g.chunks_per_slice, SLICE_THREADS, 0, st>>>(g);      // scan + copy + emulation-prevention count
   return 1;
 }
 int launch_slice_copy_ep(const FrameCtx& f, cudaStream_t st) {

@@ -51,7 +51,7 @@ def test_intra_bit_exact(w, h, qp):
     assert all(g.is_key for g in got)
 
 
-@pytest.mark.parametrize("w,h,slice_rows", [(64, 48, 1), (160, 96, 1), (160, 96, 2), (320, 192, 3), (130, 70, 100)])
+@pytest.mark.parametrize("w,h,slice_rows", [(64, 48, 1), (160, 96, 1), (160, 96, 2), (320, 192, 3), (130, 70, 100), (64, 48, 0), (320, 192, 0), (640, 368, 0), (1280, 720, 0)])
 def test_p_frames_bit_exact(w, h, slice_rows):
     frames = [synth.desktop(w, h, t) for t in range(5)]
     got, ref, grec, rrec = encode_both(w, h, frames, qp=30, slice_rows=slice_rows)
@@ -278,16 +278,17 @@ def test_paintover_burst_bit_exact():
             assert min(qps[5:8]) == 20, qps
 
 
-@pytest.mark.parametrize("w,h,mbs", [(320, 192, 7), (320, 192, 10), (130, 70, 3), (640, 368, 40), (320, 192, -1)])
-def test_idr_subrow_slices_bit_exact(w, h, mbs):
+@pytest.mark.parametrize("w,h,mbs,slice_rows", [(320, 192, 7, 0), (320, 192, 10, 1), (130, 70, 3, 0), (640, 368, 40, 3), (320, 192, -1, 1), (320, 192, -1, 0), (320, 192, 0, 2)])
+def test_idr_subrow_slices_bit_exact(w, h, mbs, slice_rows):
     """IDR pictures cut into slices shorter than a macroblock row (b2v_settings.idr_slice_mbs): left/top availability, nC
-    contexts, Intra4x4 mode prediction and first_mb_in_slice all follow the finer slice grid; P pictures keep whole rows."""
+    contexts, Intra4x4 mode prediction and first_mb_in_slice all follow the finer slice grid; P pictures keep `slice_rows` whole rows
+    (0 = the default rule: 8), and with idr_slice_mbs < 0 the IDR pictures do too (rows of a slice then form a wavefront)."""
     frames = natural_frames(w, h)[:1] + [synth.desktop(w, h, 1), synth.desktop(w, h, 2), synth.noise(w, h, 7)]
-    enc = oracle.RefEncoder(w, h, 1)
+    enc = oracle.RefEncoder(w, h, slice_rows)
     enc.set_idr_slice_mbs(mbs)
     idr_at = (0, 3)
     ref = [enc.encode_bgra(f, i in idr_at, rc_mode=1, qp=27) for i, f in enumerate(frames)]
-    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=27, idr_slice_mbs=mbs) as s:
+    with Session(w, h, rc_mode=N.B2V_RC_CQP, crf=27, idr_slice_mbs=mbs, slice_rows=slice_rows) as s:
         for i, f in enumerate(frames):
             if i == 3:
                 s.flush()
@@ -307,7 +308,7 @@ def test_idr_subrow_slices_bit_exact(w, h, mbs):
 def test_idr_subrow_slices_striped_bit_exact():
     w, h = 320, 192
     frames = [synth.desktop(w, h, t) for t in range(3)]
-    enc = oracle.RefEncoder(w, h, 1)
+    enc = oracle.RefEncoder(w, h)              # default slicing: one slice per stripe in P pictures
     enc.set_idr_slice_mbs(6)
     enc.set_stripes(4)
     ref, tabs = [], []

@@ -26,7 +26,7 @@ def c2_frames():
 
 def oracle_stream(frames, n, stripe_rows=0):
     oracle.set_threads(0)
-    enc = oracle.RefEncoder(W, H, 1)
+    enc = oracle.RefEncoder(W, H)            # default slicing, as the session's: 8-row slices (one per stripe in striped mode), IDR pictures sub-row
     if stripe_rows:
         enc.set_stripes(stripe_rows)
     target = int(KBPS * 1000 / FPS)

@@ -48,7 +48,7 @@ def frames_with_static_top(w, h, n):
     return frames
 
 
-@pytest.mark.parametrize("w,h,stripe_rows,slice_rows", [(320, 200, 4, 1), (320, 200, 4, 2), (320, 200, 6, 3), (192, 112, 1, 1), (640, 360, 8, 1)])
+@pytest.mark.parametrize("w,h,stripe_rows,slice_rows", [(320, 200, 4, 1), (320, 200, 4, 2), (320, 200, 6, 3), (192, 112, 1, 1), (640, 360, 8, 1), (320, 200, 4, 0), (640, 360, 6, 0)])
 def test_stripes_bit_exact(w, h, stripe_rows, slice_rows):
     frames = frames_with_static_top(w, h, 5)
     got, ref, grec, rrec = run_both(w, h, frames, stripe_rows, slice_rows, idr_at=(0, 3))

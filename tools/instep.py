@@ -19,7 +19,8 @@ out = {"env": os.environ.get("B2V_CSC", "default")}
 
 
 def run(flags, label):
-    with Session(W, H, fps=60.0, rc_mode=N.B2V_RC_CBR, bitrate_kbps=20000, ring_slots=16, flags=flags, collect=False) as s:
+    with Session(W, H, fps=60.0, rc_mode=N.B2V_RC_CBR, bitrate_kbps=20000, ring_slots=16, flags=flags, collect=False,
+                 slice_rows=int(os.environ.get("B2V_SLICE_ROWS", "0"))) as s:
         for i, f in enumerate(frames):
             s.resident_upload(i, f)
         for k in range(64):
