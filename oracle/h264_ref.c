@@ -1102,6 +1102,7 @@ static int rc_initial_qp(int64_t target_bits, int mbs) {
   return per_mb >= 400 ? 22 : per_mb >= 200 ? 26 : per_mb >= 100 ? 30 : per_mb >= 50 ? 34 : per_mb >= 25 ? 38 : 42;
 }
 /* Quantiser step in Q6 (64 * 2^(qp/6)): the P-picture model is  bits(qp) = X / QS[qp]. */
+#define RC_DEBT_PICTURES 32
 static const int32_t RC_QS[52] = {
   64, 72, 81, 91, 102, 114, 128, 144, 161, 181, 203, 228, 256, 287, 323, 362, 406, 456, 512, 575, 645, 724, 813, 912, 1024, 1149,
   1290, 1448, 1625, 1825, 2048, 2299, 2580, 2896, 3251, 3649, 4096, 4598, 5161, 5793, 6502, 7298, 8192, 9195, 10321, 11585, 13004,
@@ -1169,6 +1170,10 @@ static void rc_step(const enc_t* e, struct rcfb* out, const struct rcfb* prev, c
       } else if (hi * 100 < lim * 88 && full <= 0) {
         qt = qp_used - ((hi * 2 < lim && full < -2 * T) ? 2 : 1);
       }
+      /* debt: spikes the two-picture rule lets through (a scroll that restarts every N pictures, recurring cuts) pile up in the
+       * bucket; while it holds more than RC_DEBT_PICTURES pictures' worth, a picture that coded anything makes the quantiser one
+       * step coarser whatever the last two pictures say — and (rule above) it gets finer again only once the bucket is empty */
+      if (full > RC_DEBT_PICTURES * T && coded && qt <= qp_used) qt = qp_used + 1;
       q = clip3(base - 2, base + 4, qt);
     }
     n.qp = clip3(RC_QP_MIN, RC_QP_MAX, q);

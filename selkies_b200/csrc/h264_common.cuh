@@ -44,7 +44,7 @@ struct RcState {
   int32_t scan_done;       // slice-scan blocks that have finished this picture (the last one runs the rate-control step)
   long long pic_bits;      // RBSP bits of the picture just scanned (rate-control step -> AuHeader.total_bits)
 };
-constexpr int RC_QP_MIN = 10, RC_QP_MAX = 51, RC_STATIC_PARK = 1 << 20;
+constexpr int RC_QP_MIN = 10, RC_QP_MAX = 51, RC_STATIC_PARK = 1 << 20, RC_DEBT_PICTURES = 32;
 // quantiser step in Q6 (64 * 2^(qp/6)); complexity X = bits * rc_qs[qp]
 __device__ const int32_t rc_qs[52] = {
   64, 72, 81, 91, 102, 114, 128, 144, 161, 181, 203, 228, 256, 287, 323, 362, 406, 456, 512, 575, 645, 724, 813, 912, 1024, 1149,

@@ -278,6 +278,9 @@ __device__ __forceinline__ void rc_step(const FrameCtx& f, int qp_used, long lon
       } else if (hi * 100 < lim * 88 && full <= 0) {
         qt = qp_used - ((hi * 2 < lim && full < -2 * T) ? 2 : 1);
       }
+      // debt (oracle rc_step): while the bucket holds more than RC_DEBT_PICTURES pictures' worth of overspend — recurring spikes the
+      // two-picture rule lets through — a picture that coded anything makes the quantiser one step coarser
+      if (full > (long long)RC_DEBT_PICTURES * T && coded && qt <= qp_used) qt = qp_used + 1;
       q = clip3i(base - 2, base + 4, qt);
     }
     n.qp = clip3i(RC_QP_MIN, RC_QP_MAX, q);
