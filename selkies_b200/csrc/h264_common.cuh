@@ -54,7 +54,7 @@ __device__ const int32_t rc_qs[52] = {
 struct ChunkAgg; struct ChunkInc;
 struct FrameCtx {          // everything a kernel needs about the picture being coded
   int cw, ch, mbw, mbh, slice_rows, n_slices;   // n_slices: of THIS picture
-  int seg_cols;            // > 0 (IDR pictures with slice_rows == 1 only): slices of seg_cols macroblocks inside a row — the macroblocks
+  int seg_cols;            // > 0 (IDR pictures): slices of seg_cols macroblocks inside a row, whatever slice_rows is — the macroblocks
                            // of an intra slice are a serial chain, so shorter slices shorten the chain; 0 = whole rows
   int idr, rc_mode, qp_fixed;
   int paint_trigger, paint_qp, paint_burst;   // paint-over: `paint_burst` refinement pictures after `paint_trigger` all-skipped pictures (0 = off)

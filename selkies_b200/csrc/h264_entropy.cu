@@ -6,12 +6,14 @@
 //   k_cavlc_mb    one warp per macroblock, one LANE per residual block (27 blocks): each lane sizes its
 //                 block, a warp prefix-sum places it, then it writes its codes with shared-memory atomicOr;
 //                 result: a private bit string per macroblock (+ P_Skip decision, mvd from 8.4.1.3 prediction)
-//   k_slice_scan  one block per slice: block-wide scans give every macroblock its bit offset and its mb_skip_run
-//   k_slice_copy  8 threads per macroblock: bit strings are shifted into the slice RBSP (atomicOr), whole picture in parallel
-//   k_slice_ep    one block per slice: counts the emulation-prevention bytes the slice will need
+//   k_slice_build one block per chunk of up to 256 macroblocks of a slice: local scans + a decoupled look-back over the chunks of
+//                 the slice give every macroblock its bit offset and its mb_skip_run; 8 threads per macroblock shift the bit
+//                 strings into the slice RBSP (atomicOr); the chunk that finishes last counts the slice's emulation-prevention
+//                 bytes; the last block of the picture runs the rate-control step
 //   k_pack_au     one block per slice: prefix over slice sizes, emulation prevention (parallel rule: a 03 is
 //                 inserted before byte i iff byte<=3 and the run of zero bytes before it is even and >=2),
-//                 start codes + NAL headers, AuHeader, and the frame-level rate-controller update.
+//                 start codes + NAL headers, AuHeader, band table.
+// (k_slice_build_v1 — one block per slice, the three phases in sequence — is kept for A/B runs: B2V_SLICE_KERNEL=v1.)
 // CPU restatement: oracle/h264_ref.c cavlc_block(), code_slice(), nal_write(), rc_update().
 #include "h264_common.cuh"
 #include "h264_cavlc.cuh"

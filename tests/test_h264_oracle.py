@@ -51,6 +51,20 @@ def test_slicing(slice_rows):
     run(96, 80, [synth.bars(96, 80, t) for t in range(4)], 26, slice_rows)
 
 
+def test_default_slicing_decodes_and_saves_bits():
+    """slice_rows = 0: P pictures in 8-row slices (P_Skip infers moving vectors inside a slice), IDR pictures in sub-row slices /
+    one slice per row.  A scrolling picture must cost clearly less than with one row per slice, and the key frame the same."""
+    w, h = 640, 368                                                       # 23 macroblock rows: slices of 8, 8, 7
+    frames = [synth.desktop(w, h, t) for t in range(5)]
+    a8, _ = run(w, h, frames, 30, 0, idr_at=(0, 3))
+    a1, _ = run(w, h, frames, 30, 1, idr_at=(0, 3))
+    assert len(a8[0]) == len(a1[0]) and len(a8[3]) == len(a1[3])          # IDR slicing does not depend on slice_rows
+    assert sum(len(a8[i]) for i in (1, 2, 4)) < 0.9 * sum(len(a1[i]) for i in (1, 2, 4))
+    n_p_slices = sum(1 for n in split_nals(a8[1]) if (n[0] & 31) == 1)
+    assert n_p_slices == 3
+    run(1280, 720, [synth.desktop(1280, 720, t) for t in range(3)], 33, 0)   # 45 rows, IDR in two segments per row
+
+
 def test_cropped_sizes():
     run(130, 70, [synth.gradient(130, 70, t) for t in range(3)], 24)     # coded 144x80, crop both ways
     run(16, 16, [synth.noise(16, 16, 4), synth.noise(16, 16, 5)], 20)     # one macroblock
